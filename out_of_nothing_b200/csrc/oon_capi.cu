@@ -1,0 +1,888 @@
+// oon_capi.cu — the C ABI of include/oon_gpu.h: world handle, device memory, step orchestration,
+// NCCL exchange.  Host-side only; the kernels are in oon_kernels.cu.
+//
+// Reference interface replaced: OON::Model::World (/root/reference/src/app/model/World.hpp:82-158) and the
+// model part of OONApp::updates_for_next_frame (/root/reference/src/app/OON.cpp:1083-1095).
+#include "oon_internal.cuh"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace oon;
+
+// ------------------------------------------------------------------------------------------------
+// NCCL through dlopen: a single-GPU world never needs the library.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    std::string error;
+    bool load() {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) { error = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+        GetUniqueId = reinterpret_cast<decltype(GetUniqueId)>(dlsym(lib, "ncclGetUniqueId"));
+        CommInitRank = reinterpret_cast<decltype(CommInitRank)>(dlsym(lib, "ncclCommInitRank"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(dlsym(lib, "ncclCommDestroy"));
+        AllGather = reinterpret_cast<decltype(AllGather)>(dlsym(lib, "ncclAllGather"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(dlsym(lib, "ncclGetErrorString"));
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather || !GetErrorString) {
+            error = "libnccl.so.2 lacks a required symbol";
+            lib = nullptr;
+            return false;
+        }
+        return true;
+    }
+};
+NcclApi g_nccl;
+std::string g_create_error;
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// the handle
+// ------------------------------------------------------------------------------------------------
+struct SoAStorage {
+    BodySoA d{};
+    uint32_t cap = 0;
+};
+
+struct oon_world {
+    int device = 0;
+    int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_a = nullptr, ev_b = nullptr;
+
+    oon_props props{};
+    int math_mode = OON_MATH_FAST;
+
+    // partition of the world: rank g owns the contiguous index block [g*block, min(n_total,(g+1)*block))
+    uint64_t n_total = 0;     // bodies in the whole world (host view; refreshed from the device after sweeps)
+    uint32_t block = 0;       // slots per rank (multiple of TS); slots == block
+    uint32_t n_local = 0;     // host view of the live local count
+    bool has_mortals = false; // any body with lifetime > 0 or a non-unlimited non-positive lifetime
+    float rmax = 0.f;         // >= every radius in the world
+
+    SoAStorage soa[2];        // [cur] is live; the other one is the sweep target
+    int cur = 0;
+    float* tiles = nullptr;   // [nranks*block/TS][4][TS] exchange buffer
+    float4* partial = nullptr; size_t partial_cap = 0;   // [nchunks][block]
+    float4* scratch4 = nullptr;                          // player-only reaction buffer, one float4 per slot
+    size_t tiles_cap_slots = 0;                          // slots the exchange buffer (and scratch4) can hold
+    float2* kick = nullptr; uint32_t kick_cap = 0; bool kick_valid = false;
+    uint32_t* d_n = nullptr;  // live local bodies (device)
+    uint32_t* d_removed_count = nullptr;
+    unsigned long long* counters = nullptr;   // C_COUNT
+    void* sweep_temp = nullptr; size_t sweep_temp_bytes = 0;
+    int* sweep_scratch = nullptr; uint32_t sweep_scratch_cap = 0;
+    uint32_t* removed_idx = nullptr; uint32_t removed_cap = 0;
+    oon_body_f32* aos_dev = nullptr; size_t aos_cap = 0;   // staging for upload/download
+    float* xyr_dev = nullptr; size_t xyr_cap = 0;
+    CaptureBuf cap{};
+
+    bool tiles_fresh = false;       // exchange buffer matches the SoA state
+    uint64_t steps = 0;             // since last drain
+    uint64_t launches = 0;
+    uint32_t chunk_target = 20000000u;
+
+    int sticky = OON_OK;
+    std::string error;
+};
+
+namespace {
+
+int fail(oon_world* w, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (w) { w->error = buf; if (code == OON_ERR_CUDA || code == OON_ERR_NCCL) w->sticky = code; }
+    else g_create_error = buf;
+    return code;
+}
+
+#define CU(w, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(w, OON_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+#define NC(w, call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(w, OON_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); } while (0)
+#define CHECK_W(w) do { if (!(w)) return OON_ERR_INVALID; if ((w)->sticky != OON_OK) return (w)->sticky; if (cudaSetDevice((w)->device) != cudaSuccess) return fail(w, OON_ERR_CUDA, "cudaSetDevice(%d) failed", (w)->device); } while (0)
+
+template <class T>
+int dev_alloc(oon_world* w, T** p, size_t count) {
+    *p = nullptr;
+    if (!count) return OON_OK;
+    CU(w, cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
+    return OON_OK;
+}
+
+void soa_free(SoAStorage& s) {
+    cudaFree(s.d.p); cudaFree(s.d.v); cudaFree(s.d.T); cudaFree(s.d.life); cudaFree(s.d.mass); cudaFree(s.d.r);
+    cudaFree(s.d.density); cudaFree(s.d.color); cudaFree(s.d.flags); cudaFree(s.d.thrust);
+    s = SoAStorage{};
+}
+
+int soa_alloc(oon_world* w, SoAStorage& s, uint32_t cap) {
+    soa_free(s);
+    int rc;
+    if ((rc = dev_alloc(w, &s.d.p, cap))) return rc;
+    if ((rc = dev_alloc(w, &s.d.v, cap))) return rc;
+    if ((rc = dev_alloc(w, &s.d.T, cap))) return rc;
+    if ((rc = dev_alloc(w, &s.d.life, cap))) return rc;
+    if ((rc = dev_alloc(w, &s.d.mass, cap))) return rc;
+    if ((rc = dev_alloc(w, &s.d.r, cap))) return rc;
+    if ((rc = dev_alloc(w, &s.d.density, cap))) return rc;
+    if ((rc = dev_alloc(w, &s.d.color, cap))) return rc;
+    if ((rc = dev_alloc(w, &s.d.flags, cap))) return rc;
+    if ((rc = dev_alloc(w, &s.d.thrust, cap))) return rc;
+    s.cap = cap;
+    return OON_OK;
+}
+
+#define COPY_FIELD(w, f, n) CU(w, cudaMemcpyAsync(dst.d.f, src.d.f, size_t(n) * sizeof(*dst.d.f), cudaMemcpyDeviceToDevice, (w)->stream))
+int soa_copy(oon_world* w, SoAStorage& dst, const SoAStorage& src, uint32_t n) {
+    if (!n) return OON_OK;
+    COPY_FIELD(w, p, n); COPY_FIELD(w, v, n); COPY_FIELD(w, T, n); COPY_FIELD(w, life, n); COPY_FIELD(w, mass, n);
+    COPY_FIELD(w, r, n); COPY_FIELD(w, density, n); COPY_FIELD(w, color, n); COPY_FIELD(w, flags, n); COPY_FIELD(w, thrust, n);
+    return OON_OK;
+}
+
+uint32_t round_up(uint64_t x, uint32_t m) { return uint32_t((x + m - 1) / m * m); }
+
+// Lay the world out for `n_total` bodies: block size, SoA capacity, exchange buffer.  Keeps the first
+// `keep` local bodies of the current SoA.
+int layout(oon_world* w, uint64_t n_total, uint32_t keep) {
+    const uint32_t block = std::max<uint32_t>(TS, round_up((n_total + w->nranks - 1) / w->nranks, TS));
+    if (uint64_t(block) * w->nranks > 0x7fffff00ull) return fail(w, OON_ERR_INVALID, "world too large: %llu bodies", (unsigned long long)n_total);
+    if (block > w->soa[w->cur].cap) {
+        // a single-GPU world gets head-room so that add_bodies rarely reallocates
+        const uint32_t cap = w->nranks == 1 ? round_up(uint64_t(block) + block / 2, TS) : block;
+        SoAStorage fresh;
+        int rc = soa_alloc(w, fresh, cap);
+        if (rc) return rc;
+        if (keep) { rc = soa_copy(w, fresh, w->soa[w->cur], keep); if (rc) return rc; CU(w, cudaStreamSynchronize(w->stream)); }
+        soa_free(w->soa[w->cur]);
+        soa_free(w->soa[w->cur ^ 1]);
+        w->soa[w->cur] = fresh;
+    }
+    // exchange buffer (+ the player-only reaction scratch, one float4 per slot)
+    const size_t need_slots = size_t(w->nranks) * (w->nranks == 1 ? w->soa[w->cur].cap : block);
+    if (need_slots > w->tiles_cap_slots) {
+        cudaFree(w->tiles); cudaFree(w->scratch4);
+        w->tiles = nullptr; w->scratch4 = nullptr; w->tiles_cap_slots = 0;
+        int rc = dev_alloc(w, &w->tiles, need_slots * 4);
+        if (rc) return rc;
+        if ((rc = dev_alloc(w, &w->scratch4, need_slots))) return rc;
+        w->tiles_cap_slots = need_slots;
+    }
+    w->block = block;
+    w->n_total = n_total;
+    const uint64_t lo = uint64_t(w->rank) * block;
+    w->n_local = n_total > lo ? uint32_t(std::min<uint64_t>(block, n_total - lo)) : 0u;
+    w->tiles_fresh = false;
+    return OON_OK;
+}
+
+uint32_t total_tiles(const oon_world* w) { return uint32_t(uint64_t(w->block) * w->nranks / TS); }
+
+void chunking(const oon_world* w, uint32_t& nchunks, uint32_t& tiles_per_chunk) {
+    const uint32_t ntiles = total_tiles(w);
+    const uint64_t total_slots = uint64_t(ntiles) * TS;
+    uint64_t want = (w->chunk_target + total_slots - 1) / total_slots;   // depends on the world size only, never on the sharding
+    want = std::max<uint64_t>(1, std::min<uint64_t>(want, ntiles));
+    tiles_per_chunk = uint32_t((ntiles + want - 1) / want);
+    nchunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
+}
+
+int ensure_partial(oon_world* w, uint32_t nchunks) {
+    const size_t need = size_t(nchunks) * w->block;
+    if (need > w->partial_cap) {
+        cudaFree(w->partial); w->partial = nullptr; w->partial_cap = 0;
+        int rc = dev_alloc(w, &w->partial, need);
+        if (rc) return rc;
+        w->partial_cap = need;
+    }
+    return OON_OK;
+}
+
+int ensure_aos(oon_world* w, size_t n) {
+    if (n > w->aos_cap) {
+        cudaFree(w->aos_dev); w->aos_dev = nullptr; w->aos_cap = 0;
+        const size_t cap = n + n / 2 + 64;
+        int rc = dev_alloc(w, &w->aos_dev, cap);
+        if (rc) return rc;
+        w->aos_cap = cap;
+    }
+    return OON_OK;
+}
+
+StepParams step_params(const oon_world* w, float dt) {
+    StepParams sp{};
+    sp.dt = dt;
+    sp.friction = w->props.friction;
+    sp.gravity = float(w->props.gravity);
+    sp.repulsion = w->props.repulsion_stiffness;
+    sp.gravity_mode = w->props.gravity_mode;
+    sp.collision_on = w->props.collision_mode != OON_COLLISION_OFF;
+    sp.n2n = w->props.interact_n2n != 0;
+    sp.full_matrix = w->props.loop_mode == OON_LOOP_FULL_MATRIX;
+    sp.exact = w->math_mode == OON_MATH_EXACT;
+    return sp;
+}
+
+float* tiles_local(oon_world* w) { return w->tiles + size_t(w->rank) * w->block * 4; }
+
+// Timing scaffold for oon_step_profiled: class -> accumulated ms
+struct Prof {
+    bool on = false;
+    float ms[4] = {0, 0, 0, 0};
+    uint32_t launches[4] = {0, 0, 0, 0};
+};
+
+template <class F>
+int timed(oon_world* w, Prof* prof, int cls, F&& body) {
+    if (prof && prof->on) CU(w, cudaEventRecord(w->ev_a, w->stream));
+    int launched = 0;
+    int rc = body(launched);
+    if (rc) return rc;
+    w->launches += uint64_t(launched);
+    if (prof && prof->on) {
+        CU(w, cudaEventRecord(w->ev_b, w->stream));
+        CU(w, cudaEventSynchronize(w->ev_b));
+        float ms = 0; CU(w, cudaEventElapsedTime(&ms, w->ev_a, w->ev_b));
+        prof->ms[cls] += ms; prof->launches[cls] += uint32_t(launched);
+    }
+    return OON_OK;
+}
+
+int exchange(oon_world* w, Prof* prof) {
+    if (w->nranks == 1) return OON_OK;
+    return timed(w, prof, 2, [&](int& launched) -> int {
+        const size_t count = size_t(w->block) * 4;
+        NC(w, g_nccl.AllGather(tiles_local(w), w->tiles, count, ncclFloat, w->comm, w->stream));
+        launched = 1;
+        return OON_OK;
+    });
+}
+
+int do_intrinsic_pack(oon_world* w, const StepParams& sp, bool intrinsic, Prof* prof) {
+    int rc = timed(w, prof, 1, [&](int& launched) -> int {
+        launched = launch_intrinsic_pack(w->stream, w->soa[w->cur].d, w->d_n, w->block, tiles_local(w), sp, intrinsic, w->counters);
+        CU(w, cudaGetLastError());
+        return OON_OK;
+    });
+    if (rc) return rc;
+    rc = exchange(w, prof);
+    if (rc) return rc;
+    w->tiles_fresh = true;
+    return OON_OK;
+}
+
+int do_interact(oon_world* w, const StepParams& sp, uint32_t& nchunks_out, Prof* prof) {
+    uint32_t nchunks = 1, tpc = total_tiles(w);
+    if (sp.n2n && !sp.exact) chunking(w, nchunks, tpc);
+    int rc = ensure_partial(w, nchunks);
+    if (rc) return rc;
+    nchunks_out = nchunks;
+    return timed(w, prof, 0, [&](int& launched) -> int {
+        if (sp.n2n)
+            launched = launch_interact(w->stream, w->tiles, total_tiles(w), nchunks, tpc, uint32_t(w->rank) * w->block, w->block, w->d_n,
+                                       w->soa[w->cur].d, w->rmax, sp, w->partial, w->counters, w->cap);
+        else
+            launched = launch_interact_player_only(w->stream, w->tiles, total_tiles(w), uint32_t(w->rank) * w->block, w->block, w->d_n,
+                                                   nullptr, w->soa[w->cur].d, sp, w->partial, w->scratch4, w->counters, w->cap);
+        CU(w, cudaGetLastError());
+        return OON_OK;
+    });
+}
+
+int ensure_kick(oon_world* w) {
+    if (w->cap.capacity == 0) return OON_OK;          // kick trace rides on the debug switch
+    if (w->kick_cap < w->block) {
+        cudaFree(w->kick); w->kick = nullptr; w->kick_cap = 0;
+        int rc = dev_alloc(w, &w->kick, w->block);
+        if (rc) return rc;
+        w->kick_cap = w->block;
+    }
+    return OON_OK;
+}
+
+int do_integrate(oon_world* w, const StepParams& sp, uint32_t nchunks, bool apply_pairwise, bool do_global, bool fuse_next, Prof* prof) {
+    int rc = ensure_kick(w);
+    if (rc) return rc;
+    rc = timed(w, prof, 1, [&](int& launched) -> int {
+        launched = launch_integrate(w->stream, w->soa[w->cur].d, w->d_n, w->block, w->partial, nchunks, sp, apply_pairwise, do_global,
+                                    fuse_next, tiles_local(w), (apply_pairwise && w->cap.capacity) ? w->kick : nullptr, w->counters);
+        CU(w, cudaGetLastError());
+        return OON_OK;
+    });
+    if (rc) return rc;
+    if (apply_pairwise && w->cap.capacity) w->kick_valid = true;
+    if (do_global || apply_pairwise) w->tiles_fresh = false;
+    if (fuse_next) { rc = exchange(w, prof); if (rc) return rc; w->tiles_fresh = true; }
+    return OON_OK;
+}
+
+int do_sweep(oon_world* w, uint32_t player_ndx, Prof* prof) {
+    if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "expired-body sweep on a sharded world is not implemented in this build");
+    const uint32_t slots = w->block;
+    SoAStorage& other = w->soa[w->cur ^ 1];
+    if (other.cap < w->soa[w->cur].cap) { int rc = soa_alloc(w, other, w->soa[w->cur].cap); if (rc) return rc; }
+    const size_t tb = sweep_temp_bytes(w->soa[w->cur].cap);
+    if (tb > w->sweep_temp_bytes) {
+        cudaFree(w->sweep_temp); w->sweep_temp = nullptr;
+        CU(w, cudaMalloc(&w->sweep_temp, tb)); w->sweep_temp_bytes = tb;
+    }
+    if (w->sweep_scratch_cap < w->soa[w->cur].cap) {
+        cudaFree(w->sweep_scratch); w->sweep_scratch = nullptr;
+        int rc = dev_alloc(w, &w->sweep_scratch, size_t(3) * w->soa[w->cur].cap); if (rc) return rc;
+        w->sweep_scratch_cap = w->soa[w->cur].cap;
+    }
+    if (w->removed_cap < w->soa[w->cur].cap) {
+        cudaFree(w->removed_idx); w->removed_idx = nullptr;
+        int rc = dev_alloc(w, &w->removed_idx, w->soa[w->cur].cap); if (rc) return rc;
+        w->removed_cap = w->soa[w->cur].cap;
+    }
+    int rc = timed(w, prof, 3, [&](int& launched) -> int {
+        CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));
+        launched = launch_sweep(w->stream, w->soa[w->cur].d, other.d, w->d_n, slots, player_ndx, w->sweep_temp, w->sweep_temp_bytes,
+                                w->sweep_scratch, w->removed_idx, w->removed_cap, w->d_removed_count, w->counters);
+        CU(w, cudaGetLastError());
+        return OON_OK;
+    });
+    if (rc) return rc;
+    w->cur ^= 1;
+    w->tiles_fresh = false;
+    return OON_OK;
+}
+
+// Refresh the host's idea of the body count after device-side removals.
+int sync_count(oon_world* w) {
+    if (!w->has_mortals || w->nranks > 1) return OON_OK;
+    uint32_t n = 0;
+    CU(w, cudaMemcpyAsync(&n, w->d_n, sizeof n, cudaMemcpyDeviceToHost, w->stream));
+    CU(w, cudaStreamSynchronize(w->stream));
+    w->n_local = n;
+    w->n_total = n;
+    return OON_OK;
+}
+
+int step_impl(oon_world* w, float dt, uint32_t nsteps, Prof* prof) {
+    if (!nsteps || !w->block) { w->steps += nsteps; return OON_OK; }
+    const StepParams sp = step_params(w, dt);
+    const bool sweep = w->has_mortals;
+    // Frame k: intrinsic+pack -> (all-gather) -> interact -> integrate.  Without mortal bodies the
+    // integrate kernel of frame k also runs frame k+1's intrinsic+pack (one pass over the SoA, one launch).
+    int rc = do_intrinsic_pack(w, sp, true, prof);
+    if (rc) return rc;
+    for (uint32_t k = 0; k < nsteps; ++k) {
+        uint32_t nchunks = 1;
+        if ((rc = do_interact(w, sp, nchunks, prof))) return rc;
+        const bool fuse = !sweep && (k + 1 < nsteps);
+        if ((rc = do_integrate(w, sp, nchunks, true, true, fuse, prof))) return rc;
+        if (sweep) {
+            if ((rc = do_sweep(w, 0, prof))) return rc;
+            if (k + 1 < nsteps && (rc = do_intrinsic_pack(w, sp, true, prof))) return rc;
+        }
+    }
+    w->steps += nsteps;
+    return OON_OK;
+}
+
+bool mortal(float lifetime) { return lifetime > 0.f || (lifetime != LIFETIME_UNLIMITED && lifetime <= 0.f); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// exported entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int oon_abi_version(void) { return OON_ABI_VERSION; }
+
+const char* oon_last_error(const oon_world* w) { return w ? w->error.c_str() : g_create_error.c_str(); }
+
+int oon_props_default(oon_props* out) {
+    if (!out) return OON_ERR_INVALID;
+    std::memset(out, 0, sizeof *out);
+    out->friction = 0.03f;                       // World.cpp:42-50
+    out->gravity_mode = OON_GRAVITY_HYPERBOLIC;
+    out->gravity = 6.6743e-11;
+    out->interact_n2n = 0;
+    out->collision_mode = OON_COLLISION_GLIDE_THROUGH;
+    out->repulsion_stiffness = 0.0;
+    out->loop_mode = OON_LOOP_HALF_MATRIX;
+    return OON_OK;
+}
+
+int oon_nccl_unique_id(void* out_id) {
+    if (!out_id) return OON_ERR_INVALID;
+    if (!g_nccl.load()) return fail(nullptr, OON_ERR_NCCL, "%s", g_nccl.error.c_str());
+    static_assert(sizeof(ncclUniqueId) == OON_NCCL_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId id;
+    ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, OON_ERR_NCCL, "ncclGetUniqueId failed: %s", g_nccl.GetErrorString(r));
+    std::memcpy(out_id, &id, sizeof id);
+    return OON_OK;
+}
+
+static int create_common(int device, int rank, int nranks, const void* id, oon_world** out) {
+    if (!out || nranks < 1 || rank < 0 || rank >= nranks) return fail(nullptr, OON_ERR_INVALID, "bad arguments to oon_create");
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, OON_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path");
+    }
+    if (device < 0 || device >= count) return fail(nullptr, OON_ERR_INVALID, "device %d out of range (have %d)", device, count);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, OON_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return fail(nullptr, OON_ERR_NO_DEVICE, "device %d is sm_%d%d; the kernels are built for sm_100a only", device, prop.major, prop.minor);
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, OON_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+
+    auto* w = new oon_world;
+    w->device = device; w->rank = rank; w->nranks = nranks;
+    oon_props_default(&w->props);
+    if (const char* e = getenv("OON_CHUNK_TARGET")) { long v = atol(e); if (v > 0) w->chunk_target = uint32_t(v); }
+    auto bail = [&](int code) { std::string msg = w->error; oon_destroy(w); g_create_error = msg; return code; };
+#define CUB_(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { w->error = std::string(#call) + " failed: " + cudaGetErrorString(e_); return bail(OON_ERR_CUDA); } } while (0)
+    CUB_(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    CUB_(cudaEventCreate(&w->ev_start)); CUB_(cudaEventCreate(&w->ev_stop));
+    CUB_(cudaEventCreate(&w->ev_a)); CUB_(cudaEventCreate(&w->ev_b));
+    CUB_(cudaMalloc(&w->d_n, sizeof(uint32_t))); CUB_(cudaMemset(w->d_n, 0, sizeof(uint32_t)));
+    CUB_(cudaMalloc(&w->d_removed_count, sizeof(uint32_t))); CUB_(cudaMemset(w->d_removed_count, 0, sizeof(uint32_t)));
+    CUB_(cudaMalloc(&w->counters, sizeof(unsigned long long) * C_COUNT));
+    CUB_(cudaMemset(w->counters, 0, sizeof(unsigned long long) * C_COUNT));
+#undef CUB_
+    if (nranks > 1) {
+        if (!id) { w->error = "sharded world needs an NCCL unique id"; return bail(OON_ERR_INVALID); }
+        if (!g_nccl.load()) { w->error = g_nccl.error; return bail(OON_ERR_NCCL); }
+        ncclUniqueId uid; std::memcpy(&uid, id, sizeof uid);
+        ncclResult_t r = g_nccl.CommInitRank(&w->comm, nranks, uid, rank);
+        if (r != ncclSuccess) { w->error = std::string("ncclCommInitRank failed: ") + g_nccl.GetErrorString(r); return bail(OON_ERR_NCCL); }
+    }
+    *out = w;
+    return OON_OK;
+}
+
+int oon_create(int device, oon_world** out) { return create_common(device, 0, 1, nullptr, out); }
+int oon_create_sharded(int device, int rank, int nranks, const void* nccl_unique_id, oon_world** out) {
+    return create_common(device, rank, nranks, nccl_unique_id, out);
+}
+
+int oon_destroy(oon_world* w) {
+    if (!w) return OON_ERR_INVALID;
+    cudaSetDevice(w->device);
+    if (w->stream) cudaStreamSynchronize(w->stream);
+    if (w->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(w->comm);
+    soa_free(w->soa[0]); soa_free(w->soa[1]);
+    cudaFree(w->tiles); cudaFree(w->partial); cudaFree(w->scratch4); cudaFree(w->kick); cudaFree(w->d_n); cudaFree(w->d_removed_count);
+    cudaFree(w->counters); cudaFree(w->sweep_temp); cudaFree(w->sweep_scratch); cudaFree(w->removed_idx); cudaFree(w->aos_dev);
+    cudaFree(w->xyr_dev); cudaFree(w->cap.coll); cudaFree(w->cap.touch);
+    if (w->ev_start) cudaEventDestroy(w->ev_start);
+    if (w->ev_stop) cudaEventDestroy(w->ev_stop);
+    if (w->ev_a) cudaEventDestroy(w->ev_a);
+    if (w->ev_b) cudaEventDestroy(w->ev_b);
+    if (w->stream) cudaStreamDestroy(w->stream);
+    cudaGetLastError();
+    delete w;
+    return OON_OK;
+}
+
+int oon_set_props(oon_world* w, const oon_props* p) {
+    CHECK_W(w);
+    if (!p) return fail(w, OON_ERR_INVALID, "null props");
+    if (p->gravity_mode > OON_GRAVITY_EXPERIMENTAL) return fail(w, OON_ERR_INVALID, "gravity_mode %u out of range", p->gravity_mode);
+    if (p->collision_mode > OON_COLLISION_GLIDE_THROUGH) return fail(w, OON_ERR_INVALID, "collision_mode %u out of range", p->collision_mode);
+    if (p->loop_mode > OON_LOOP_FULL_MATRIX) return fail(w, OON_ERR_INVALID, "loop_mode %u out of range", p->loop_mode);
+    w->props = *p;
+    return OON_OK;
+}
+int oon_get_props(const oon_world* w, oon_props* out) {
+    if (!w || !out) return OON_ERR_INVALID;
+    *out = w->props;
+    return OON_OK;
+}
+int oon_set_math_mode(oon_world* w, int mode) {
+    CHECK_W(w);
+    if (mode != OON_MATH_FAST && mode != OON_MATH_EXACT) return fail(w, OON_ERR_INVALID, "math mode %d out of range", mode);
+    w->math_mode = mode;
+    return OON_OK;
+}
+int oon_get_math_mode(const oon_world* w, int* mode) {
+    if (!w || !mode) return OON_ERR_INVALID;
+    *mode = w->math_mode;
+    return OON_OK;
+}
+
+int oon_upload(oon_world* w, const oon_body_f32* bodies, uint64_t n) {
+    CHECK_W(w);
+    if (n && !bodies) return fail(w, OON_ERR_INVALID, "null body table");
+    bool mortals = false; float rmax = 0.f;
+    for (uint64_t i = 0; i < n; ++i) { mortals |= mortal(bodies[i].lifetime); rmax = std::max(rmax, bodies[i].r); }
+    if (mortals && w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "bodies with finite lifetimes on a sharded world are not implemented in this build");
+    int rc = layout(w, n, 0);
+    if (rc) return rc;
+    w->has_mortals = mortals; w->rmax = rmax;
+    const uint64_t lo = uint64_t(w->rank) * w->block;
+    if (w->n_local) {
+        if ((rc = ensure_aos(w, w->n_local))) return rc;
+        CU(w, cudaMemcpyAsync(w->aos_dev, bodies + lo, size_t(w->n_local) * sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
+        w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, 0, w->n_local);
+        CU(w, cudaGetLastError());
+    }
+    CU(w, cudaMemcpyAsync(w->d_n, &w->n_local, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+    CU(w, cudaStreamSynchronize(w->stream));     // the caller may reuse `bodies` immediately (pageable memory)
+    w->kick_valid = false;
+    return OON_OK;
+}
+
+int oon_upload_f64(oon_world* w, const oon_body_f64* bodies, uint64_t n) {
+    CHECK_W(w);
+    if (n && !bodies) return fail(w, OON_ERR_INVALID, "null body table");
+    std::vector<oon_body_f32> tmp(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        const oon_body_f64& s = bodies[i]; oon_body_f32& d = tmp[i];
+        std::memset(&d, 0, sizeof d);
+        d.gravity_immunity = s.gravity_immunity; d.free_color = s.free_color;
+        d.lifetime = float(s.lifetime); d.r = float(s.r); d.density = float(s.density);
+        d.px = float(s.px); d.py = float(s.py); d.vx = float(s.vx); d.vy = float(s.vy);
+        d.T = s.T; d.color = s.color; d.mass = float(s.mass);
+        d.thrust_up = s.thrust_up; d.thrust_down = s.thrust_down; d.thrust_left = s.thrust_left; d.thrust_right = s.thrust_right;
+    }
+    return oon_upload(w, tmp.data(), n);
+}
+
+// Gather the whole world into aos_dev (device), in host order.  Sharded: all-gather of the packed blocks.
+static int gather_aos(oon_world* w, uint64_t* n_out) {
+    int rc = sync_count(w);
+    if (rc) return rc;
+    const uint64_t n = w->n_total;
+    if (w->nranks == 1) {
+        if ((rc = ensure_aos(w, n))) return rc;
+        w->launches += launch_pack_f32(w->stream, w->soa[w->cur].d, w->aos_dev, 0, uint32_t(n));
+        CU(w, cudaGetLastError());
+    } else {
+        const size_t per = size_t(w->block);
+        if ((rc = ensure_aos(w, per * w->nranks))) return rc;
+        w->launches += launch_pack_f32(w->stream, w->soa[w->cur].d, w->aos_dev + per * w->rank, 0, w->n_local);
+        CU(w, cudaGetLastError());
+        NC(w, g_nccl.AllGather(w->aos_dev + per * w->rank, w->aos_dev, per * sizeof(oon_body_f32), ncclChar, w->comm, w->stream));
+    }
+    *n_out = n;
+    return OON_OK;
+}
+
+int oon_download(oon_world* w, oon_body_f32* out, uint64_t capacity, uint64_t* n_out) {
+    CHECK_W(w);
+    uint64_t n = 0;
+    int rc = gather_aos(w, &n);
+    if (rc) return rc;
+    if (n_out) *n_out = n;
+    if (n > capacity) return fail(w, OON_ERR_CAPACITY, "download needs room for %llu bodies, got %llu", (unsigned long long)n, (unsigned long long)capacity);
+    if (n && !out) return fail(w, OON_ERR_INVALID, "null output");
+    if (n) CU(w, cudaMemcpyAsync(out, w->aos_dev, size_t(n) * sizeof(oon_body_f32), cudaMemcpyDeviceToHost, w->stream));
+    CU(w, cudaStreamSynchronize(w->stream));
+    return OON_OK;
+}
+
+int oon_download_f64(oon_world* w, oon_body_f64* out, uint64_t capacity, uint64_t* n_out) {
+    CHECK_W(w);
+    std::vector<oon_body_f32> tmp(w->n_total);
+    uint64_t n = 0;
+    int rc = oon_download(w, tmp.data(), tmp.size(), &n);
+    if (n_out) *n_out = n;
+    if (rc) return rc;
+    if (n > capacity) return fail(w, OON_ERR_CAPACITY, "download needs room for %llu bodies", (unsigned long long)n);
+    for (uint64_t i = 0; i < n; ++i) {
+        const oon_body_f32& s = tmp[i]; oon_body_f64& d = out[i];
+        std::memset(&d, 0, sizeof d);
+        d.gravity_immunity = s.gravity_immunity; d.free_color = s.free_color;
+        d.lifetime = s.lifetime; d.r = s.r; d.density = s.density; d.px = s.px; d.py = s.py; d.vx = s.vx; d.vy = s.vy;
+        d.T = s.T; d.color = s.color; d.mass = s.mass;
+        d.thrust_up = s.thrust_up; d.thrust_down = s.thrust_down; d.thrust_left = s.thrust_left; d.thrust_right = s.thrust_right;
+    }
+    return OON_OK;
+}
+
+int oon_download_render(oon_world* w, float* xyr, uint64_t capacity, uint64_t* n_out) {
+    CHECK_W(w);
+    int rc = sync_count(w);
+    if (rc) return rc;
+    const uint64_t n = w->n_total;
+    if (n_out) *n_out = n;
+    if (n > capacity) return fail(w, OON_ERR_CAPACITY, "render download needs room for %llu bodies", (unsigned long long)n);
+    if (n && !xyr) return fail(w, OON_ERR_INVALID, "null output");
+    const size_t per = size_t(w->block) * 3;
+    const size_t need = per * w->nranks;
+    if (need > w->xyr_cap) {
+        cudaFree(w->xyr_dev); w->xyr_dev = nullptr; w->xyr_cap = 0;
+        if ((rc = dev_alloc(w, &w->xyr_dev, need + need / 2))) return rc;
+        w->xyr_cap = need + need / 2;
+    }
+    w->launches += launch_render_pack(w->stream, w->soa[w->cur].d, w->d_n, w->block, w->xyr_dev + per * w->rank);
+    CU(w, cudaGetLastError());
+    if (w->nranks > 1) NC(w, g_nccl.AllGather(w->xyr_dev + per * w->rank, w->xyr_dev, per, ncclFloat, w->comm, w->stream));
+    if (n) CU(w, cudaMemcpyAsync(xyr, w->xyr_dev, size_t(n) * 3 * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
+    CU(w, cudaStreamSynchronize(w->stream));
+    return OON_OK;
+}
+
+int oon_body_count(oon_world* w, uint64_t* n_out) {
+    CHECK_W(w);
+    if (!n_out) return fail(w, OON_ERR_INVALID, "null output");
+    int rc = sync_count(w);
+    if (rc) return rc;
+    *n_out = w->n_total;
+    return OON_OK;
+}
+
+int oon_add_bodies(oon_world* w, const oon_body_f32* bodies, uint64_t k) {
+    CHECK_W(w);
+    if (!k) return OON_OK;
+    if (!bodies) return fail(w, OON_ERR_INVALID, "null body table");
+    if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "add_bodies on a sharded world: re-upload the table instead");
+    int rc = sync_count(w);
+    if (rc) return rc;
+    const uint32_t old_n = w->n_local;
+    if ((rc = layout(w, uint64_t(old_n) + k, old_n))) return rc;
+    if ((rc = ensure_aos(w, k))) return rc;
+    for (uint64_t i = 0; i < k; ++i) { w->has_mortals |= mortal(bodies[i].lifetime); w->rmax = std::max(w->rmax, bodies[i].r); }
+    CU(w, cudaMemcpyAsync(w->aos_dev, bodies, size_t(k) * sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
+    w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, old_n, uint32_t(k));
+    CU(w, cudaGetLastError());
+    CU(w, cudaMemcpyAsync(w->d_n, &w->n_local, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+    CU(w, cudaStreamSynchronize(w->stream));
+    return OON_OK;
+}
+
+int oon_get_body(oon_world* w, uint64_t ndx, oon_body_f32* out) {
+    CHECK_W(w);
+    if (!out) return fail(w, OON_ERR_INVALID, "null output");
+    int rc = sync_count(w);
+    if (rc) return rc;
+    if (ndx >= w->n_total) return fail(w, OON_ERR_INVALID, "body index %llu out of range (%llu bodies)", (unsigned long long)ndx, (unsigned long long)w->n_total);
+    if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "get_body on a sharded world: use oon_download");
+    if ((rc = ensure_aos(w, 1))) return rc;
+    w->launches += launch_pack_f32(w->stream, w->soa[w->cur].d, w->aos_dev, uint32_t(ndx), 1);
+    CU(w, cudaGetLastError());
+    CU(w, cudaMemcpyAsync(out, w->aos_dev, sizeof(oon_body_f32), cudaMemcpyDeviceToHost, w->stream));
+    CU(w, cudaStreamSynchronize(w->stream));
+    return OON_OK;
+}
+
+int oon_set_body(oon_world* w, uint64_t ndx, const oon_body_f32* in) {
+    CHECK_W(w);
+    if (!in) return fail(w, OON_ERR_INVALID, "null input");
+    int rc = sync_count(w);
+    if (rc) return rc;
+    if (ndx >= w->n_total) return fail(w, OON_ERR_INVALID, "body index %llu out of range (%llu bodies)", (unsigned long long)ndx, (unsigned long long)w->n_total);
+    if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "set_body on a sharded world: re-upload the table instead");
+    if ((rc = ensure_aos(w, 1))) return rc;
+    w->has_mortals |= mortal(in->lifetime); w->rmax = std::max(w->rmax, in->r);
+    CU(w, cudaMemcpyAsync(w->aos_dev, in, sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
+    w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, uint32_t(ndx), 1);
+    CU(w, cudaGetLastError());
+    CU(w, cudaStreamSynchronize(w->stream));
+    w->tiles_fresh = false;
+    return OON_OK;
+}
+
+int oon_remove_body(oon_world* w, uint64_t ndx) {
+    CHECK_W(w);
+    int rc = sync_count(w);
+    if (rc) return rc;
+    if (ndx >= w->n_total) return fail(w, OON_ERR_INVALID, "body index %llu out of range (%llu bodies)", (unsigned long long)ndx, (unsigned long long)w->n_total);
+    if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "remove_body on a sharded world: re-upload the table instead");
+    // erase(begin + ndx): shift the tail down by one, field by field, through the spare SoA buffer
+    const uint32_t n = w->n_local, tail = n - uint32_t(ndx) - 1;
+    SoAStorage& cur = w->soa[w->cur];
+    SoAStorage& other = w->soa[w->cur ^ 1];
+    if (other.cap < cur.cap) { if ((rc = soa_alloc(w, other, cur.cap))) return rc; }
+    if (tail) {
+#define SHIFT(f) do { CU(w, cudaMemcpyAsync(other.d.f, cur.d.f + ndx + 1, size_t(tail) * sizeof(*cur.d.f), cudaMemcpyDeviceToDevice, w->stream)); \
+                      CU(w, cudaMemcpyAsync(cur.d.f + ndx, other.d.f, size_t(tail) * sizeof(*cur.d.f), cudaMemcpyDeviceToDevice, w->stream)); } while (0)
+        SHIFT(p); SHIFT(v); SHIFT(T); SHIFT(life); SHIFT(mass); SHIFT(r); SHIFT(density); SHIFT(color); SHIFT(flags); SHIFT(thrust);
+#undef SHIFT
+    }
+    w->n_local = n - 1; w->n_total = n - 1;
+    CU(w, cudaMemcpyAsync(w->d_n, &w->n_local, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+    CU(w, cudaStreamSynchronize(w->stream));
+    w->tiles_fresh = false;
+    return OON_OK;
+}
+
+int oon_step(oon_world* w, float dt, uint32_t nsteps) {
+    CHECK_W(w);
+    return step_impl(w, dt, nsteps, nullptr);
+}
+
+int oon_step_profiled(oon_world* w, float dt, uint32_t nsteps, float ms[4], uint32_t launches[4]) {
+    CHECK_W(w);
+    Prof prof; prof.on = true;
+    int rc = step_impl(w, dt, nsteps, &prof);
+    if (ms) std::memcpy(ms, prof.ms, sizeof prof.ms);
+    if (launches) std::memcpy(launches, prof.launches, sizeof prof.launches);
+    return rc;
+}
+
+int oon_update_intrinsic(oon_world* w, float dt) {
+    CHECK_W(w);
+    if (!w->block) return OON_OK;
+    return do_intrinsic_pack(w, step_params(w, dt), true, nullptr);
+}
+
+int oon_update_pairwise(oon_world* w, float dt) {
+    CHECK_W(w);
+    if (!w->block) return OON_OK;
+    const StepParams sp = step_params(w, dt);
+    int rc;
+    if (!w->tiles_fresh && (rc = do_intrinsic_pack(w, sp, false, nullptr))) return rc;
+    uint32_t nchunks = 1;
+    if ((rc = do_interact(w, sp, nchunks, nullptr))) return rc;
+    return do_integrate(w, sp, nchunks, true, false, false, nullptr);
+}
+
+int oon_update_global(oon_world* w, float dt) {
+    CHECK_W(w);
+    if (!w->block) return OON_OK;
+    return do_integrate(w, step_params(w, dt), 1, false, true, false, nullptr);
+}
+
+int oon_sweep_expired(oon_world* w, uint64_t player_ndx) {
+    CHECK_W(w);
+    if (!w->block || !w->has_mortals) return OON_OK;
+    return do_sweep(w, uint32_t(player_ndx), nullptr);
+}
+
+int oon_synchronize(oon_world* w) {
+    CHECK_W(w);
+    CU(w, cudaStreamSynchronize(w->stream));
+    return OON_OK;
+}
+
+int oon_drain_events(oon_world* w, oon_events* out) {
+    CHECK_W(w);
+    if (!out) return fail(w, OON_ERR_INVALID, "null output");
+    unsigned long long c[C_COUNT];
+    CU(w, cudaMemcpyAsync(c, w->counters, sizeof c, cudaMemcpyDeviceToHost, w->stream));
+    CU(w, cudaMemsetAsync(w->counters, 0, sizeof(unsigned long long) * C_CAPTURE_COLL, w->stream));   // capture cursors live on
+    CU(w, cudaStreamSynchronize(w->stream));
+    out->steps = w->steps; w->steps = 0;
+    out->collisions = c[C_COLLISIONS]; out->touches = c[C_TOUCHES]; out->player_touches = c[C_PLAYER_TOUCHES];
+    out->terminated = c[C_TERMINATED]; out->removed = c[C_REMOVED];
+    return OON_OK;
+}
+
+int oon_timer_start(oon_world* w) {
+    CHECK_W(w);
+    CU(w, cudaEventRecord(w->ev_start, w->stream));
+    return OON_OK;
+}
+int oon_timer_stop(oon_world* w, float* elapsed_ms) {
+    CHECK_W(w);
+    if (!elapsed_ms) return fail(w, OON_ERR_INVALID, "null output");
+    CU(w, cudaEventRecord(w->ev_stop, w->stream));
+    CU(w, cudaEventSynchronize(w->ev_stop));
+    CU(w, cudaEventElapsedTime(elapsed_ms, w->ev_start, w->ev_stop));
+    return OON_OK;
+}
+
+int oon_launch_count(const oon_world* w, uint64_t* n_out) {
+    if (!w || !n_out) return OON_ERR_INVALID;
+    *n_out = w->launches;
+    return OON_OK;
+}
+
+int oon_measure_fp32_peak(int device, double* tflops_out) {
+    if (!tflops_out) return OON_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, OON_ERR_NO_DEVICE, "cudaSetDevice(%d) failed", device); }
+    const float t = measure_fp32_peak_tflops(nullptr);
+    if (t <= 0) return fail(nullptr, OON_ERR_CUDA, "FFMA probe failed");
+    *tflops_out = t;
+    return OON_OK;
+}
+int oon_measure_copy_bandwidth(int device, double* gbs_out) {
+    if (!gbs_out) return OON_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, OON_ERR_NO_DEVICE, "cudaSetDevice(%d) failed", device); }
+    const float g = measure_copy_gbs(nullptr);
+    if (g <= 0) return fail(nullptr, OON_ERR_CUDA, "copy probe failed");
+    *gbs_out = g;
+    return OON_OK;
+}
+
+int oon_debug_capture_pairs(oon_world* w, uint64_t capacity) {
+    CHECK_W(w);
+    CU(w, cudaStreamSynchronize(w->stream));
+    cudaFree(w->cap.coll); cudaFree(w->cap.touch);
+    w->cap = CaptureBuf{};
+    if (capacity) {
+        if (capacity > 0x7fffffffull) return fail(w, OON_ERR_INVALID, "capture capacity too large");
+        int rc;
+        if ((rc = dev_alloc(w, &w->cap.coll, capacity))) return rc;
+        if ((rc = dev_alloc(w, &w->cap.touch, capacity))) return rc;
+        w->cap.capacity = uint32_t(capacity);
+    }
+    CU(w, cudaMemset(w->counters + C_CAPTURE_COLL, 0, 2 * sizeof(unsigned long long)));
+    w->kick_valid = false;
+    return OON_OK;
+}
+
+int oon_debug_fetch_pairs(oon_world* w, int which, uint32_t* pairs, uint64_t capacity, uint64_t* n_out) {
+    CHECK_W(w);
+    if (which != 0 && which != 1) return fail(w, OON_ERR_INVALID, "which must be 0 or 1");
+    if (!w->cap.capacity) return fail(w, OON_ERR_INVALID, "pair capture is off");
+    unsigned long long cnt = 0;
+    const int ci = which == 0 ? C_CAPTURE_COLL : C_CAPTURE_TOUCH;
+    CU(w, cudaMemcpyAsync(&cnt, w->counters + ci, sizeof cnt, cudaMemcpyDeviceToHost, w->stream));
+    CU(w, cudaStreamSynchronize(w->stream));
+    if (n_out) *n_out = cnt;
+    if (cnt > w->cap.capacity) return fail(w, OON_ERR_CAPACITY, "pair capture overflowed: %llu pairs, capacity %u", cnt, w->cap.capacity);
+    if (cnt > capacity) return fail(w, OON_ERR_CAPACITY, "output too small for %llu pairs", cnt);
+    if (cnt) {
+        if (!pairs) return fail(w, OON_ERR_INVALID, "null output");
+        CU(w, cudaMemcpyAsync(pairs, which == 0 ? w->cap.coll : w->cap.touch, size_t(cnt) * sizeof(uint2), cudaMemcpyDeviceToHost, w->stream));
+    }
+    CU(w, cudaMemsetAsync(w->counters + ci, 0, sizeof(unsigned long long), w->stream));
+    CU(w, cudaStreamSynchronize(w->stream));
+    return OON_OK;
+}
+
+int oon_debug_fetch_kick(oon_world* w, float* dv, uint64_t capacity, uint64_t* n_out) {
+    CHECK_W(w);
+    if (!w->kick_valid) return fail(w, OON_ERR_INVALID, "no kick recorded: enable oon_debug_capture_pairs and run a pairwise pass first");
+    if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "kick trace on a sharded world");
+    const uint64_t n = w->n_local;
+    if (n_out) *n_out = n;
+    if (n > capacity) return fail(w, OON_ERR_CAPACITY, "output too small for %llu bodies", (unsigned long long)n);
+    if (n) CU(w, cudaMemcpyAsync(dv, w->kick, size_t(n) * sizeof(float2), cudaMemcpyDeviceToHost, w->stream));
+    CU(w, cudaStreamSynchronize(w->stream));
+    return OON_OK;
+}
+
+int oon_debug_fetch_removed(oon_world* w, uint32_t* idx, uint64_t capacity, uint64_t* n_out) {
+    CHECK_W(w);
+    uint32_t cnt = 0;
+    CU(w, cudaMemcpyAsync(&cnt, w->d_removed_count, sizeof cnt, cudaMemcpyDeviceToHost, w->stream));
+    CU(w, cudaStreamSynchronize(w->stream));
+    if (n_out) *n_out = cnt;
+    if (cnt > capacity) return fail(w, OON_ERR_CAPACITY, "output too small for %u indices", cnt);
+    if (cnt) {
+        if (!idx) return fail(w, OON_ERR_INVALID, "null output");
+        CU(w, cudaMemcpyAsync(idx, w->removed_idx, size_t(cnt) * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+        CU(w, cudaStreamSynchronize(w->stream));
+    }
+    return OON_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// oon_internal.cuh — shared declarations between the kernels (oon_kernels.cu) and the C ABI (oon_capi.cu).
+// sm_100a only.  Names follow the reference's domain (bodies, sources, targets, tiles, shards).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/oon_gpu.h"
+
+namespace oon {
+
+// ---- geometry of the source exchange buffer ---------------------------------------------------
+// Sources live in "tiles" of TS bodies laid out as four contiguous arrays {x[TS], y[TS], m[TS], r[TS]}
+// (AoSoA).  One tile is one 4 KiB TMA bulk copy into shared memory and lands exactly in the
+// layout the packed-FP32 inner loop reads (two sources per 64-bit register pair).
+constexpr int TS = 256;                    // bodies per tile
+constexpr int TILE_FLOATS = 4 * TS;        // floats per tile
+constexpr int TILE_BYTES = TILE_FLOATS * 4;
+constexpr int CTA_THREADS = 256;
+
+// A dead slot (padding, or a body with lifetime == 0) is parked far away with no mass and a
+// negative radius: it attracts nothing, never collides and never comes near anything.
+constexpr float DEAD_COORD = 1.0e18f;
+constexpr float DEAD_RADIUS = -1.0e30f;
+
+constexpr float EPS_COLLISION = 50000000.0f / 10;   // World.hpp:91, World.cpp:315 (a float constant)
+constexpr float THRUST_UNSET = 2e31f;               // Math::unset<float>() as stored in the fixtures
+constexpr float LIFETIME_UNLIMITED = -1.0f;         // Entity::Unlimited, Entity.hpp:34
+
+// per-body flag bits (device SoA)
+enum : uint8_t { F_IMMUNE = 1, F_FREE_COLOR = 2, F_PLAYER = 4 };
+
+// counters kept on the device (uint64 each)
+enum { C_COLLISIONS = 0, C_TOUCHES, C_PLAYER_TOUCHES, C_TERMINATED, C_REMOVED, C_CAPTURE_COLL, C_CAPTURE_TOUCH, C_COUNT };
+
+// One step's constant parameters, passed by value to the kernels.
+struct StepParams {
+    float dt;
+    float friction;
+    float gravity;              // G as float (NumType(props.gravity))
+    double repulsion;           // repulsion_stiffness (double in the reference)
+    uint32_t gravity_mode;      // OON_GRAVITY_*
+    uint32_t collision_on;      // collision_mode != Off
+    uint32_t n2n;               // interact_n2n
+    uint32_t full_matrix;       // loop_mode == Full_Matrix
+    uint32_t exact;             // OON_MATH_EXACT
+};
+
+// Device view of one shard's private state (structure of arrays, local index order == host order).
+struct BodySoA {
+    float2* p;          // position
+    float2* v;          // velocity
+    float* T;           // temperature
+    float* life;        // lifetime
+    float* mass;
+    float* r;           // radius
+    float* density;
+    uint32_t* color;
+    uint8_t* flags;     // F_*
+    float4* thrust;     // up, down, left, right
+};
+
+struct CaptureBuf {
+    uint2* coll;        // (target, source)
+    uint2* touch;
+    uint32_t capacity;  // 0 = capture off
+};
+
+// ---- launchers (oon_kernels.cu) ------------------------------------------------------------------
+// All take the stream to launch on and return the number of kernels launched.
+
+// AoS (60 B records) <-> SoA
+int launch_unpack_f32(cudaStream_t st, const oon_body_f32* aos, BodySoA soa, uint32_t first, uint32_t count);
+int launch_pack_f32(cudaStream_t st, BodySoA soa, oon_body_f32* aos, uint32_t first, uint32_t count);
+
+// update_intrinsic + pack the shard's slice of the exchange buffer.  `tiles_local` points at the first
+// tile of this shard; slots in [n, slots) are written dead.
+int launch_intrinsic_pack(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint32_t slots, float* tiles_local,
+                          StepParams sp, bool do_intrinsic, unsigned long long* counters);
+
+// The all-pairs pass.  tiles: whole gathered buffer (ntiles tiles).  Targets = local slots
+// [0, slots) living at global slot target_base.  partial: [nchunks][slots] float4 {ax, ay, touch_count, -}.
+int launch_interact(cudaStream_t st, const float* tiles, uint32_t ntiles, uint32_t nchunks, uint32_t tiles_per_chunk,
+                    uint32_t target_base, uint32_t slots, const uint32_t* d_n_local, BodySoA soa, float rmax,
+                    StepParams sp, float4* partial, unsigned long long* counters, CaptureBuf cap);
+
+// interact_n2n == false: only body 0 is a source (and, in half-matrix mode, the target of everyone).
+int launch_interact_player_only(cudaStream_t st, const float* tiles, uint32_t ntiles, uint32_t target_base,
+                                uint32_t slots, const uint32_t* d_n_local, const uint32_t* d_n_total, BodySoA soa,
+                                StepParams sp, float4* partial, float4* scratch, unsigned long long* counters, CaptureBuf cap);
+
+// update_global (+ touch heat + kick application), optionally fused with the next step's
+// update_intrinsic + pack.  kick_out (optional) receives the velocity change of the pairwise pass.
+int launch_integrate(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint32_t slots, const float4* partial,
+                     uint32_t nchunks, StepParams sp, bool apply_pairwise, bool do_global, bool fuse_next_intrinsic,
+                     float* tiles_local, float2* kick_out, unsigned long long* counters);
+
+// The caller's expired-body sweep (OON.cpp:1089-1095) as a stable device compaction from `src` into `dst`.
+// d_n is updated in place.  removed_idx (optional, capacity removed_cap) gets the indices at removal time.
+size_t sweep_temp_bytes(uint32_t slots);
+int launch_sweep(cudaStream_t st, BodySoA src, BodySoA dst, uint32_t* d_n, uint32_t slots, uint32_t player_ndx,
+                 void* temp, size_t temp_bytes, int* scratch_i32 /* 3*slots ints */, uint32_t* removed_idx,
+                 uint32_t removed_cap, uint32_t* d_removed_count, unsigned long long* counters);
+
+// render read set: {x, y, r} per body
+int launch_render_pack(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint32_t slots, float* xyr);
+
+// microbenchmarks
+float measure_fp32_peak_tflops(cudaStream_t st);
+float measure_copy_gbs(cudaStream_t st);
+
+}  // namespace oon

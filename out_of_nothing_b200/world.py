@@ -1,0 +1,223 @@
+"""Python host mirror of the reference's ``OON::Model::World`` over the C ABI.
+
+Same names and argument meaning as /root/reference/src/app/model/World.hpp:82-158
+(``props``, ``add_body``, ``remove_body``, ``update_intrinsic/_pairwise/_global``,
+``loop_mode``/``set_loop_mode``) plus the caller-side sweep of OON.cpp:1089-1095, so that
+parity tests read like the reference's own regression runs.  All physics happens in
+liboon_gpu.so on the device; this file only marshals arguments.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import numpy as np
+
+from . import capi
+from .capi import BODY_F32, Events, OonError, Props
+
+
+class Properties:
+    """Live view of ``World::props`` (World.hpp:59-69): attribute writes go straight to the device handle."""
+
+    _names = ("friction", "gravity_mode", "gravity", "interact_n2n", "collision_mode", "repulsion_stiffness", "loop_mode")
+
+    def __init__(self, world: "World"):
+        object.__setattr__(self, "_w", world)
+
+    def __getattr__(self, name):
+        if name not in self._names:
+            raise AttributeError(name)
+        p = self._w._get_props()
+        v = getattr(p, name)
+        return bool(v) if name == "interact_n2n" else v
+
+    def __setattr__(self, name, value):
+        if name not in self._names:
+            raise AttributeError(name)
+        p = self._w._get_props()
+        setattr(p, name, int(value) if name in ("gravity_mode", "interact_n2n", "collision_mode", "loop_mode") else value)
+        self._w._set_props(p)
+
+
+class World:
+    """One world on one GPU, or one shard of a world sharded over ``nranks`` processes."""
+
+    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1, nccl_id: Optional[bytes] = None):
+        self._L = capi.load()
+        self._h = ctypes.c_void_p()
+        if nranks == 1:
+            rc = self._L.oon_create(device, ctypes.byref(self._h))
+        else:
+            rc = self._L.oon_create_sharded(device, rank, nranks, nccl_id, ctypes.byref(self._h))
+        if rc:
+            raise OonError(rc, (self._L.oon_last_error(None) or b"").decode())
+        self.props = Properties(self)
+        self.rank, self.nranks, self.device = rank, nranks, device
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc: int):
+        if rc:
+            raise OonError(rc, (self._L.oon_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.oon_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _get_props(self) -> Props:
+        p = Props()
+        self._check(self._L.oon_get_props(self._h, ctypes.byref(p)))
+        return p
+
+    def _set_props(self, p: Props):
+        self._check(self._L.oon_set_props(self._h, ctypes.byref(p)))
+
+    # ------------------------------------------------------------------ knobs
+    def set_props(self, **kw):
+        p = self._get_props()
+        for k, v in kw.items():
+            if k not in Properties._names:
+                raise AttributeError(k)
+            setattr(p, k, int(v) if k in ("gravity_mode", "interact_n2n", "collision_mode", "loop_mode") else v)
+        self._set_props(p)
+
+    def loop_mode(self) -> int:
+        return self._get_props().loop_mode
+
+    def set_loop_mode(self, mode: int):
+        self.set_props(loop_mode=mode)
+
+    @property
+    def math_mode(self) -> int:
+        m = ctypes.c_int()
+        self._check(self._L.oon_get_math_mode(self._h, ctypes.byref(m)))
+        return m.value
+
+    @math_mode.setter
+    def math_mode(self, mode: int):
+        self._check(self._L.oon_set_math_mode(self._h, mode))
+
+    # ------------------------------------------------------------------ body table
+    def upload(self, bodies: np.ndarray):
+        bodies = np.ascontiguousarray(bodies)
+        assert bodies.dtype.itemsize == 60, "expected 60-byte float-build records"
+        self._check(self._L.oon_upload(self._h, bodies.ctypes.data, bodies.shape[0]))
+
+    def upload_ptr(self, ptr: int, n: int):
+        """Upload from a raw host pointer (e.g. pinned memory owned by the caller)."""
+        self._check(self._L.oon_upload(self._h, ptr, n))
+
+    def download(self) -> np.ndarray:
+        n = self.entity_count()
+        out = np.zeros(n, BODY_F32)
+        got = ctypes.c_uint64()
+        self._check(self._L.oon_download(self._h, out.ctypes.data, n, ctypes.byref(got)))
+        return out[: got.value]
+
+    def download_ptr(self, ptr: int, capacity: int) -> int:
+        got = ctypes.c_uint64()
+        self._check(self._L.oon_download(self._h, ptr, capacity, ctypes.byref(got)))
+        return got.value
+
+    def download_render(self) -> np.ndarray:
+        n = self.entity_count()
+        out = np.zeros((n, 3), np.float32)
+        got = ctypes.c_uint64()
+        self._check(self._L.oon_download_render(self._h, out.ctypes.data, n, ctypes.byref(got)))
+        return out[: got.value]
+
+    def entity_count(self) -> int:
+        n = ctypes.c_uint64()
+        self._check(self._L.oon_body_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def add_body(self, body) -> int:
+        """World::add_body (World.cpp:55-70).  Returns the new body's index."""
+        rec = np.zeros(1, BODY_F32)
+        rec[0] = body
+        n = self.entity_count()
+        self._check(self._L.oon_add_bodies(self._h, rec.ctypes.data, 1))
+        return n
+
+    def add_bodies(self, bodies: np.ndarray):
+        bodies = np.ascontiguousarray(bodies)
+        self._check(self._L.oon_add_bodies(self._h, bodies.ctypes.data, bodies.shape[0]))
+
+    def remove_body(self, ndx: int):
+        """World::remove_body (World.cpp:72-78): erase, later indices shift down."""
+        self._check(self._L.oon_remove_body(self._h, ndx))
+
+    def entity(self, ndx: int) -> np.ndarray:
+        rec = np.zeros(1, BODY_F32)
+        self._check(self._L.oon_get_body(self._h, ndx, rec.ctypes.data))
+        return rec[0]
+
+    def set_entity(self, ndx: int, body):
+        rec = np.zeros(1, BODY_F32)
+        rec[0] = body
+        self._check(self._L.oon_set_body(self._h, ndx, rec.ctypes.data))
+
+    # ------------------------------------------------------------------ the hot path
+    def update_intrinsic(self, dt: float): self._check(self._L.oon_update_intrinsic(self._h, dt))
+    def update_pairwise(self, dt: float): self._check(self._L.oon_update_pairwise(self._h, dt))
+    def update_global(self, dt: float): self._check(self._L.oon_update_global(self._h, dt))
+    def sweep_expired(self, player_ndx: int = 0): self._check(self._L.oon_sweep_expired(self._h, player_ndx))
+
+    def step(self, dt: float, nsteps: int = 1):
+        """nsteps frames of OONApp::updates_for_next_frame's model part (OON.cpp:1085-1095)."""
+        self._check(self._L.oon_step(self._h, dt, nsteps))
+
+    def step_profiled(self, dt: float, nsteps: int = 1):
+        ms = (ctypes.c_float * 4)()
+        launches = (ctypes.c_uint32 * 4)()
+        self._check(self._L.oon_step_profiled(self._h, dt, nsteps, ms, launches))
+        names = ("interact", "integrate", "exchange", "sweep")
+        return {k: float(ms[i]) for i, k in enumerate(names)}, {k: int(launches[i]) for i, k in enumerate(names)}
+
+    def synchronize(self): self._check(self._L.oon_synchronize(self._h))
+
+    def drain_events(self) -> dict:
+        ev = Events()
+        self._check(self._L.oon_drain_events(self._h, ctypes.byref(ev)))
+        return {n: int(getattr(ev, n)) for n, _ in Events._fields_}
+
+    # ------------------------------------------------------------------ measurement / trace
+    def timer_start(self): self._check(self._L.oon_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = ctypes.c_float()
+        self._check(self._L.oon_timer_stop(self._h, ctypes.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        n = ctypes.c_uint64()
+        self._check(self._L.oon_launch_count(self._h, ctypes.byref(n)))
+        return n.value
+
+    def debug_capture_pairs(self, capacity: int): self._check(self._L.oon_debug_capture_pairs(self._h, capacity))
+
+    def debug_fetch_pairs(self, which: int, capacity: int = 1 << 22) -> np.ndarray:
+        out = np.zeros((capacity, 2), np.uint32)
+        n = ctypes.c_uint64()
+        self._check(self._L.oon_debug_fetch_pairs(self._h, which, out.ctypes.data, capacity, ctypes.byref(n)))
+        return out[: n.value].copy()
+
+    def debug_fetch_kick(self) -> np.ndarray:
+        n = self.entity_count()
+        out = np.zeros((n, 2), np.float32)
+        got = ctypes.c_uint64()
+        self._check(self._L.oon_debug_fetch_kick(self._h, out.ctypes.data, n, ctypes.byref(got)))
+        return out[: got.value]
+
+    def debug_fetch_removed(self, capacity: int = 1 << 20) -> np.ndarray:
+        out = np.zeros(capacity, np.uint32)
+        n = ctypes.c_uint64()
+        self._check(self._L.oon_debug_fetch_removed(self._h, out.ctypes.data, capacity, ctypes.byref(n)))
+        return out[: n.value].copy()
