@@ -1,0 +1,319 @@
+#!/usr/bin/env python3
+"""Headless benchmark of the world update (BASELINE.json metric: directed body-pair interactions / s, steps / s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4_cloud_100k] [--impl ours|reference]
+
+N > 1 is launched by the driver as
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+one rank per GPU: targets are sharded in contiguous index blocks, sources are all-gathered once per frame by the
+library's own NCCL communicator; torch.distributed only carries the NCCL id, the barriers and the max-over-ranks.
+
+Workload (default C4 of BASELINE.json, the configuration the metric and the roofline target are quoted on):
+100 000-body random cloud, gravity only (friction 0), all-pairs, hyperbolic law, dt 0.033, total size fixed as the
+GPU count grows ("strong" scaling).  Rank 0 prints ONE JSON line.
+
+A "step" = one frame: update_intrinsic + update_pairwise + update_global (+ the expired-body sweep when bodies can
+expire).  `value` = steps * N*(N-1) / device time of the K timed frames, inputs resident in HBM.  `e2e` = the same
+metric through the C ABI with host buffers: every frame uploads the body table from pinned host memory, steps once
+and downloads it again.  `--impl reference` times the oracle port of the reference's CPU path (the reference itself
+cannot be built: engine sources absent) on one host core — the reference is single-threaded by construction.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_INTERACTION = 18          # literal op count of World.cpp:271-288,304,363-364
+INTEGRATE_BYTES_PER_BODY = 77      # BASELINE.md §2 / SURVEY.md §8d
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4_cloud_100k")
+    ap.add_argument("--n", type=int, default=0, help="override the body count of the workload")
+    ap.add_argument("--math", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--no-l2-flush", action="store_true", help="time the K frames back to back in one enqueue")
+    ap.add_argument("--cpu-sample-bodies", type=int, default=0)
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.rows, self.proc, self.device_index = [], None, device_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def calibrate_cpu_rate(pyoracle, synth, workload):
+    bodies, cfg = synth.make(workload, n=2000)
+    o = pyoracle.OracleWorld(double=False)
+    o.set_props(**cfg["props"]); o.set_bodies(bodies)
+    t = o.time_steps(cfg["dt"], 2)
+    return 2 * 2000 * 1999 / t
+
+
+def run_reference(args):
+    """The reference's CPU world update (oracle port: literal restatement, same data layout) on one host core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    from out_of_nothing_b200 import synth
+    cfg_n = args.n or synth.CONFIGS[args.workload]["n"]
+    rate = calibrate_cpu_rate(pyoracle, synth, args.workload)
+    budget_s = 90.0
+    n_sample = args.cpu_sample_bodies or int(min(cfg_n, max(1000, (budget_s * rate / max(1, args.steps + args.warmup)) ** 0.5)))
+    bodies, cfg = synth.make(args.workload, n=cfg_n)
+    bodies = bodies[:n_sample]
+    o = pyoracle.OracleWorld(double=False)
+    o.set_props(**cfg["props"]); o.set_bodies(bodies)
+    o.step(cfg["dt"], args.warmup)
+    n0 = o.n
+    secs = o.time_steps(cfg["dt"], args.steps)
+    inter = args.steps * n0 * (n0 - 1)
+    value = inter / secs
+    sample = "first %d bodies of the %d-body %s world, %d frames after %d warm-up, oracle<float> (-O2 -ffp-contract=off)" % (
+        n_sample, cfg_n, args.workload, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": "body_pair_interactions_per_sec", "value": value, "unit": "interactions/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
+        "steps_per_sec": args.steps / secs, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "n_bodies": cfg_n, "sample_bodies": n_sample, "dt": cfg["dt"], **cfg["props"]},
+        "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from out_of_nothing_b200 import capi, sharding, synth
+    from out_of_nothing_b200.world import World
+
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world_size != args.gpus:
+        if world_size == 1 and args.gpus > 1:
+            print(json.dumps({"error": "--gpus %d needs torchrun with %d ranks" % (args.gpus, args.gpus)}))
+            return 2
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        idt = torch.zeros(capi.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world_size == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    bodies, cfg = synth.make(args.workload, n=args.n or None)
+    n = bodies.shape[0]
+    dt = cfg["dt"]
+    w = World(local_rank, rank, world_size, nccl_id)
+    w.set_props(**cfg["props"])
+    w.math_mode = capi.MATH_EXACT if args.math == "exact" else capi.MATH_FAST
+    w.upload(bodies)
+
+    # ---- live FP32 peak (roofline denominator) before the run, on this device
+    fp32_peak = capi.measure_fp32_peak(local_rank)
+
+    flush = None
+    if not args.no_l2_flush:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    # ---- warm-up
+    w.step(dt, max(args.warmup, 3))
+    w.synchronize()
+    n_start = w.entity_count()
+
+    # ---- timed region: device time of exactly K frames, barrier + synchronize on both sides, max over ranks
+    sampler = ClockSampler(local_rank)
+    barrier()
+    launches0 = w.launch_count()
+    sampler.start()
+    t_host0 = time.perf_counter()
+    if flush is None:
+        w.timer_start(); w.step(dt, args.steps); ms = w.timer_stop()
+    else:
+        ms = 0.0
+        for _ in range(args.steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()                      # the flush runs on torch's stream, the frame on the library's
+            w.timer_start(); w.step(dt, 1); ms += w.timer_stop()
+    barrier()
+    host_s = time.perf_counter() - t_host0
+    clocks = sampler.stop()
+    launches = w.launch_count() - launches0
+    ms = max_over_ranks(ms)
+    n_end = w.entity_count()
+    inter_per_step = sharding.interactions_per_step(n_start)     # no body of this workload can expire unless it says so
+    value = args.steps * inter_per_step / (ms * 1e-3)
+
+    # ---- per-kernel device time (events on the launching stream) for the roofline lines
+    prof_steps = 5
+    prof_ms, prof_launches = w.step_profiled(dt, prof_steps)
+    lo, hi = sharding.shard_range(n_start, rank, world_size)
+    local_inter = (hi - lo) * (n_start - 1)
+    k1_ms = prof_ms["interact"] / max(1, prof_launches["interact"])
+    k1_tflops = FLOP_PER_INTERACTION * local_inter / (k1_ms * 1e-3) * 1e-12 if k1_ms > 0 else 0.0
+    k2_ms = prof_ms["integrate"] / max(1, prof_launches["integrate"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    k2_gbs = INTEGRATE_BYTES_PER_BODY * (hi - lo) / (k2_ms * 1e-3) * 1e-9 if k2_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "interact_traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+
+    # ---- e2e: the drop-in call sequence with HOST buffers (pinned), copies inside the timed region
+    e2e_steps = max(1, min(args.e2e_steps, args.steps))
+    host_in = torch.empty(n_start * 60, dtype=torch.uint8).pin_memory()
+    host_out = torch.empty(n_start * 60, dtype=torch.uint8).pin_memory()
+    cur = w.download()
+    host_in.numpy()[:] = np.frombuffer(cur.tobytes(), dtype=np.uint8)
+    w.upload_ptr(host_in.data_ptr(), n_start); w.step(dt, 1); w.download_ptr(host_out.data_ptr(), n_start)   # warm
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        w.upload_ptr(host_in.data_ptr(), n_start)
+        w.step(dt, 1)
+        got = w.download_ptr(host_out.data_ptr(), n_start)
+        host_in, host_out = host_out, host_in               # next frame's input is this frame's output
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = e2e_steps * sharding.interactions_per_step(n_start) / e2e_s
+    h2d = 60 * n_start                                       # summed over ranks: every rank uploads its own block
+    d2h = 60 * n_start * world_size                          # every rank reads the whole table back
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on one host core, bounded sample
+    cpu = None
+    if rank == 0 and world_size == 1 and not args.skip_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import pyoracle
+        ns = args.cpu_sample_bodies or min(n, 30000)
+        o = pyoracle.OracleWorld(double=False)
+        o.set_props(**cfg["props"]); o.set_bodies(bodies[:ns])
+        cpu_steps = 2
+        secs = o.time_steps(dt, cpu_steps)
+        cpu = {"value": cpu_steps * ns * (ns - 1) / secs, "unit": "interactions/s", "cores": 1, "kind": "port",
+               "sample": "first %d bodies of the same world, %d frames, oracle<float> built -O2 -ffp-contract=off, %.1f s" % (ns, cpu_steps, secs)}
+
+    if rank == 0:
+        line = {
+            "metric": "body_pair_interactions_per_sec", "value": value, "unit": "interactions/s",
+            "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "steps_per_sec": args.steps / (ms * 1e-3),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "n_bodies": n, "n_bodies_end": n_end, "dt": dt, "math": args.math,
+                       "parallelism": "targets sharded in %d contiguous blocks, sources all-gathered per frame (NCCL)" % world_size if world_size > 1 else "single GPU",
+                       "l2": ("flushed between timed frames (256 MiB write)" if flush is not None else
+                              "not flushed; frames timed back to back"), **cfg["props"]},
+            "roofline": {"bound": "fp32", "kernel": "k_interact_fast" if args.math == "fast" else "k_interact_exact",
+                         "achieved": k1_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": k1_tflops / fp32_peak if fp32_peak else None, "traffic": traffic,
+                         "peak_source": "FFMA microbenchmark measured in this run on this device (MEASURED_PEAKS.json has no FP32 entry)",
+                         "algorithmic_flop_per_interaction": FLOP_PER_INTERACTION, "interactions_per_launch": local_inter,
+                         "ms_per_launch": k1_ms},
+            "roofline_integrate": {"bound": "hbm", "kernel": "k_integrate", "achieved": k2_gbs, "peak": hbm_peak, "unit": "GB/s",
+                                   "frac": k2_gbs / hbm_peak, "ms_per_launch": k2_ms,
+                                   "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+            "kernel_ms_per_step": {k: v / prof_steps for k, v in prof_ms.items()},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                    "call": "oon_upload(pinned host AoS) + oon_step(dt,1) + oon_download(pinned host AoS) every frame"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "host_wall_s_timed_region": host_s,
+        }
+        print(json.dumps(line), flush=True)
+    w.close()
+    if world_size > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -19,6 +19,10 @@
 
 using namespace oon;
 
+static_assert(sizeof(oon_body_f32) == 60, "oon_body_f32 must match the reference's float-build Entity");
+static_assert(sizeof(oon_body_f64) == 96, "oon_body_f64 must match the reference's double-build Entity");
+static_assert(sizeof(oon_props) == 40 && sizeof(oon_events) == 48, "ABI struct sizes");
+
 // ------------------------------------------------------------------------------------------------
 // NCCL through dlopen: a single-GPU world never needs the library.
 // ------------------------------------------------------------------------------------------------
@@ -542,6 +546,7 @@ int oon_upload(oon_world* w, const oon_body_f32* bodies, uint64_t n) {
         CU(w, cudaGetLastError());
     }
     CU(w, cudaMemcpyAsync(w->d_n, &w->n_local, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+    CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));
     CU(w, cudaStreamSynchronize(w->stream));     // the caller may reuse `bodies` immediately (pageable memory)
     w->kick_valid = false;
     return OON_OK;

@@ -1,0 +1,471 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference's golden fixtures.
+
+Contract:
+  * EXACT math mode is bit-identical to the float oracle in every field except `color`
+    (which neither restates: Phys::T_to_RGB_and_BV is absent from the reference tree).
+  * FAST math mode: collision / touch / expiry decisions and body counts identical, T bit-exact,
+    kicks and velocities within TOL_KICK_* and positions within TOL_POS_MAX per frame on identical
+    input (teacher-forced), positions within TOL_FREE_POS_* of the double oracle after the
+    reference's own 20-frame smoke horizon.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from helpers import (TC_SMOKE, TOL_FREE_POS_MAX, TOL_FREE_POS_MEDIAN, TOL_KICK_MAX, TOL_KICK_MEDIAN, TOL_POS_MAX,
+                     bodies_equal_except_color, kick_f64_sample, load_golden, make_oracle, pair_list, pos_tol, props_of, rel_err)
+from out_of_nothing_b200 import capi, snapshot, synth
+
+pytestmark = pytest.mark.gpu
+
+FAST, EXACT = capi.MATH_FAST, capi.MATH_EXACT
+DT = TC_SMOKE["dt"]
+
+
+def gpu_world(bodies, props, mode, capture=1 << 20):
+    from out_of_nothing_b200.world import World
+    w = World(0)
+    w.set_props(**{k: (int(v) if isinstance(v, bool) else v) for k, v in props.items()})
+    w.math_mode = mode
+    if capture:
+        w.debug_capture_pairs(capture)
+    w.upload(bodies)
+    return w
+
+
+def smoke_props(start, **over):
+    kw = dict(friction=TC_SMOKE["friction"], interact_n2n=True)
+    kw.update(over)
+    return props_of(start, **kw)
+
+
+# ---------------------------------------------------------------------------------------------- KAT-1
+def test_kat1_exact_mode_is_bit_identical_over_the_smoke_horizon(kat1):
+    start, end = kat1
+    props = smoke_props(start)
+    o = make_oracle(start.bodies, props, trace=True)
+    w = gpu_world(start.bodies, props, EXACT)
+    w.step(DT, TC_SMOKE["steps"]); o.step(DT, TC_SMOKE["steps"])
+    got, ref, tr = w.download(), o.bodies(), o.trace_fetch()
+    assert got.tobytes() == ref.tobytes()
+    assert (got["T"] == end.bodies["T"]).all()                      # and with the reference's own END state
+    assert pair_list(w.debug_fetch_pairs(0)) == pair_list(tr["collisions"])
+    assert pair_list(w.debug_fetch_pairs(1)) == pair_list(tr["touches"])
+    ev = w.drain_events()
+    assert (ev["steps"], ev["collisions"], ev["touches"], ev["removed"]) == (20, 3590, 322, 0)
+    assert w.entity_count() == 1010
+
+
+def test_kat1_fast_mode_teacher_forced_every_frame(kat1):
+    """Same input state each frame -> compare kick, v, p, T and the decision lists (SURVEY.md §8d parity gates).
+    v, p, T, decisions: against the float oracle (the reference's arithmetic).  The kick itself (dv of the pairwise
+    pass) is compared with the double oracle run from the same state: the float oracle adds ~1000 small kicks one by
+    one into a large v, so its own dv carries ~ulp(v)*sqrt(N) of rounding noise, more than the tolerance."""
+    start, _ = kat1
+    props = smoke_props(start)
+    o = make_oracle(start.bodies, props, trace=True)
+    w = gpu_world(start.bodies, props, FAST)
+    worst = dict(kick_med=0, kick_max=0, v_med=0, v_max=0, p_max=0)
+    for frame in range(TC_SMOKE["steps"]):
+        state = o.bodies()
+        w.upload(state)
+        od = make_oracle(state, props, double=True)
+        od.update_intrinsic(DT)
+        v0 = od.pv64()[:, 2:]
+        od.update_pairwise(DT)
+        kick_true = od.pv64()[:, 2:] - v0
+        o.trace_clear()
+        o.update_intrinsic(DT)
+        v0f = o.pv64()[:, 2:]
+        o.update_pairwise(DT)
+        kick_float_oracle = o.pv64()[:, 2:] - v0f
+        o.update_global(DT); o.sweep_expired()
+        w.step(DT, 1)
+        got, ref, tr = w.download(), o.bodies(), o.trace_fetch()
+        assert pair_list(w.debug_fetch_pairs(0)) == pair_list(tr["collisions"]), frame
+        assert pair_list(w.debug_fetch_pairs(1)) == pair_list(tr["touches"]), frame
+        assert (got["T"] == ref["T"]).all(), frame
+        assert got["lifetime"].tobytes() == ref["lifetime"].tobytes() and got["r"].tobytes() == ref["r"].tobytes()
+        ek, ev, ep = rel_err(w.debug_fetch_kick(), kick_true), rel_err(got["v"], ref["v"]), rel_err(got["p"], ref["p"])
+        assert np.median(ek) <= TOL_KICK_MEDIAN and ek.max() <= TOL_KICK_MAX, (frame, np.median(ek), ek.max())
+        assert np.median(ek) <= np.median(rel_err(kick_float_oracle, kick_true)), frame     # closer to the truth than the CPU float path
+        assert np.median(ev) <= TOL_KICK_MEDIAN and ev.max() <= TOL_KICK_MAX, (frame, np.median(ev), ev.max())
+        assert ep.max() <= TOL_POS_MAX, (frame, ep.max())
+        worst = dict(kick_med=max(worst["kick_med"], np.median(ek)), kick_max=max(worst["kick_max"], ek.max()),
+                     v_med=max(worst["v_med"], np.median(ev)), v_max=max(worst["v_max"], ev.max()), p_max=max(worst["p_max"], ep.max()))
+    print("worst teacher-forced errors:", worst)
+
+
+def test_kat1_fast_mode_free_running_vs_double_oracle(kat1):
+    start, end = kat1
+    props = smoke_props(start)
+    od = make_oracle(start.bodies, props, double=True, trace=True)
+    w = gpu_world(start.bodies, props, FAST)
+    w.step(DT, TC_SMOKE["steps"]); od.step(DT, TC_SMOKE["steps"])
+    got, tr = w.download(), od.trace_fetch()
+    e = rel_err(got["p"], od.pv64()[:, :2])
+    assert e.max() <= TOL_FREE_POS_MAX and np.median(e) <= TOL_FREE_POS_MEDIAN, (e.max(), np.median(e))
+    assert pair_list(w.debug_fetch_pairs(0)) == pair_list(tr["collisions"])
+    assert pair_list(w.debug_fetch_pairs(1)) == pair_list(tr["touches"])
+    assert (got["T"] == end.bodies["T"]).all()
+    # the CUDA fast path is no further from the double oracle than the reference's own float arithmetic is
+    of = make_oracle(start.bodies, props); of.step(DT, TC_SMOKE["steps"])
+    e_ref = rel_err(of.bodies()["p"], od.pv64()[:, :2])
+    assert np.median(e) <= 2.0 * np.median(e_ref) + 1e-9
+
+
+# ---------------------------------------------------------------------------------------------- knobs
+KNOBS = {
+    "realistic": dict(gravity_mode=2),
+    "experimental": dict(gravity_mode=3),
+    "gravity_off": dict(gravity_mode=0),
+    "full_matrix": dict(loop_mode=1),
+    "collision_off": dict(collision_mode=0),
+    "repulsion_half": dict(repulsion_stiffness=5e-10),
+    "repulsion_full_ignored": dict(repulsion_stiffness=5e-10, loop_mode=1),
+    "repulsion_realistic": dict(repulsion_stiffness=8e-10, gravity_mode=2),
+    "negative_friction": dict(friction=-0.5),
+    "strong_gravity": dict(gravity=6.6743e-8),
+}
+
+
+@pytest.mark.parametrize("name", sorted(KNOBS))
+def test_physics_knobs_exact_mode_bitwise(kat1, name):
+    start, _ = kat1
+    bodies = start.bodies.copy()
+    bodies["gravity_immunity"][5:40:7] = 1
+    props = smoke_props(start, **KNOBS[name])
+    o = make_oracle(bodies, props, trace=True)
+    w = gpu_world(bodies, props, EXACT)
+    w.step(DT, 3); o.step(DT, 3)
+    got, ref, tr = w.download(), o.bodies(), o.trace_fetch()
+    ok, field = bodies_equal_except_color(got, ref)
+    assert ok, field
+    assert pair_list(w.debug_fetch_pairs(0)) == pair_list(tr["collisions"])
+    assert pair_list(w.debug_fetch_pairs(1)) == pair_list(tr["touches"])
+
+
+@pytest.mark.parametrize("name", sorted(KNOBS))
+def test_physics_knobs_fast_mode_within_tolerance(kat1, name):
+    start, _ = kat1
+    bodies = start.bodies.copy()
+    bodies["gravity_immunity"][5:40:7] = 1
+    props = smoke_props(start, **KNOBS[name])
+    o = make_oracle(bodies, props, trace=True)
+    w = gpu_world(bodies, props, FAST)
+    w.step(DT, 1); o.step(DT, 1)
+    got, ref, tr = w.download(), o.bodies(), o.trace_fetch()
+    assert pair_list(w.debug_fetch_pairs(0)) == pair_list(tr["collisions"])
+    assert pair_list(w.debug_fetch_pairs(1)) == pair_list(tr["touches"])
+    assert (got["T"] == ref["T"]).all()
+    ev, ep = rel_err(got["v"], ref["v"]), rel_err(got["p"], ref["p"])
+    # collision_off lets overlapping pairs attract with 1/d -> near-singular kicks; the relative error of each
+    # kick is unchanged but they dominate the rms scale, so the same bound holds
+    assert np.median(ev) <= TOL_KICK_MEDIAN and ev.max() <= TOL_KICK_MAX, (np.median(ev), ev.max())
+    assert ep.max() <= pos_tol(ref, DT), (ep.max(), pos_tol(ref, DT))
+
+
+@pytest.mark.parametrize("dt", [0.0, -0.033, 0.001])
+@pytest.mark.parametrize("mode", [FAST, EXACT])
+def test_dt_zero_negative_small(kat1, dt, mode):
+    start, _ = kat1
+    props = smoke_props(start)
+    o = make_oracle(start.bodies, props)
+    w = gpu_world(start.bodies, props, mode, capture=0)
+    w.step(dt, 2); o.step(dt, 2)
+    got, ref = w.download(), o.bodies()
+    if mode == EXACT:
+        assert got.tobytes() == ref.tobytes()
+    else:
+        assert (got["T"] == ref["T"]).all()
+        assert rel_err(got["p"], ref["p"]).max() <= 2 * TOL_POS_MAX
+
+
+# ---------------------------------------------------------------------------------------------- player-only mode
+@pytest.mark.parametrize("loop_mode", [0, 1])
+@pytest.mark.parametrize("mode", [FAST, EXACT])
+def test_player_only_mode(mode, loop_mode):
+    """interact_n2n = false is the reference's default (World.cpp:47): body 0 is the only source."""
+    s = load_golden("kat2_start.state")
+    bodies = s.bodies.copy()
+    bodies["gravity_immunity"][0] = 0              # let the player feel everyone (half-matrix reaction, World.cpp:412-416)
+    props = props_of(s, friction=0.01, loop_mode=loop_mode)
+    assert not props["interact_n2n"]
+    o = make_oracle(bodies, props, trace=True)
+    w = gpu_world(bodies, props, mode)
+    w.step(DT, 5); o.step(DT, 5)
+    got, ref, tr = w.download(), o.bodies(), o.trace_fetch()
+    assert pair_list(w.debug_fetch_pairs(0)) == pair_list(tr["collisions"])
+    assert pair_list(w.debug_fetch_pairs(1)) == pair_list(tr["touches"])
+    assert got[1:].tobytes() == ref[1:].tobytes()          # every pair (0, j) uses the exact sequence in both modes
+    if mode == EXACT:
+        assert got[:1].tobytes() == ref[:1].tobytes()
+    else:                                                 # body 0's sum over N partners is tree-ordered in FAST mode
+        assert got["T"][0] == ref["T"][0]
+        assert np.abs(got["v"][0].astype(np.float64) - ref["v"][0]).max() <= 1e-5 * np.abs(ref["v"][0]).max() + 1e-3
+
+
+# ---------------------------------------------------------------------------------------------- lifetimes / sweep
+def mortal_world(n=600, seed=7):
+    b = synth.with_finite_lifetimes(synth.random_cloud(n, seed=seed), 0.5, 0.02, 0.5, seed=seed)
+    b["lifetime"][10:30] = 0.05            # a long run of consecutive expiries: exercises the erase-without-fix-up quirk
+    b["lifetime"][40] = 0.0                # already terminated at load
+    b["lifetime"][41] = -0.5               # negative but not Unlimited: swept at once, never "terminated"
+    return b
+
+
+@pytest.mark.parametrize("mode", [FAST, EXACT])
+def test_expiry_and_sweep_sequence_matches(mode):
+    bodies = mortal_world()
+    props = dict(friction=0.01, gravity_mode=1, gravity=6.6743e-11, interact_n2n=True, repulsion_stiffness=0.0, collision_mode=1, loop_mode=0)
+    o = make_oracle(bodies, props, trace=True)
+    w = gpu_world(bodies, props, mode, capture=1 << 20)
+    for frame in range(20):
+        if mode == FAST:
+            w.upload(o.bodies())                       # teacher-forced: identical input each frame
+        o.trace_clear()
+        o.step(0.033, 1)
+        w.step(0.033, 1)
+        tr = o.trace_fetch()
+        assert w.entity_count() == o.n, frame
+        assert w.debug_fetch_removed().tolist() == tr["expired"].tolist(), frame
+        got, ref = w.download(), o.bodies()
+        assert got["lifetime"].tobytes() == ref["lifetime"].tobytes() and got["r"].tobytes() == ref["r"].tobytes(), frame
+        assert (got["T"] == ref["T"]).all(), frame
+        assert pair_list(w.debug_fetch_pairs(0)) == pair_list(tr["collisions"]), frame
+        if mode == EXACT:
+            assert got.tobytes() == ref.tobytes(), frame
+    assert o.n < bodies.shape[0] - 100
+    ev = w.drain_events()
+    assert ev["removed"] == bodies.shape[0] - o.n
+
+
+@pytest.mark.parametrize("fixture,frames", [("realg_test.state", 300), ("multi_cluster_640.save", 60)])
+def test_fixture_worlds_with_finite_lifetimes_exact(fixture, frames):
+    s = load_golden(fixture)
+    assert (s.bodies["lifetime"] > 0).sum() > 0
+    props = props_of(s, interact_n2n=True)
+    o = make_oracle(s.bodies, props)
+    w = gpu_world(s.bodies, props, EXACT, capture=0)
+    done = 0
+    while done < frames:
+        w.step(DT, 20); o.step(DT, 20); done += 20
+        assert w.entity_count() == o.n
+        ok, field = bodies_equal_except_color(w.download(), o.bodies())
+        assert ok, (done, field)
+
+
+# ---------------------------------------------------------------------------------------------- sizes and edges
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 31, 255, 256, 257, 511, 513, 1500])
+def test_ragged_and_tiny_worlds(n):
+    bodies = synth.random_cloud(max(n, 1), seed=3)[:n]
+    props = dict(friction=0.03, gravity_mode=1, gravity=6.6743e-11, interact_n2n=True, repulsion_stiffness=0.0, collision_mode=1, loop_mode=0)
+    o = make_oracle(bodies, props, trace=True)
+    o.step(DT, 2)
+    ref, tr = o.bodies(), o.trace_fetch()
+    for mode in (EXACT, FAST):
+        w = gpu_world(bodies, props, mode)
+        w.step(DT, 2)
+        got = w.download()
+        assert got.shape[0] == n == w.entity_count()
+        assert pair_list(w.debug_fetch_pairs(0)) == pair_list(tr["collisions"])
+        if mode == EXACT:
+            assert got.tobytes() == ref.tobytes()
+        elif n:
+            assert (got["T"] == ref["T"]).all()
+            assert rel_err(got["v"], ref["v"]).max() <= 4 * TOL_KICK_MAX    # two free-running frames
+        w.close()
+
+
+def test_coincident_and_touching_bodies():
+    """d == 0 between distinct bodies, and pairs sitting exactly on the two decision boundaries."""
+    b = synth.random_cloud(64, seed=11)
+    b["p"][5] = b["p"][4]                                   # coincident centres: colliding, never a division by zero
+    r = float(b["r"][8] + b["r"][9])
+    b["p"][9] = b["p"][8] + np.array([r, 0], np.float32)    # d == r_t + r_s up to rounding: boundary of is_colliding
+    b["p"][11] = b["p"][10] + np.array([float(b["r"][10] + b["r"][11]) - 5e6, 0], np.float32)   # boundary of the touch test
+    props = dict(friction=0.0, gravity_mode=1, gravity=6.6743e-11, interact_n2n=True, repulsion_stiffness=0.0, collision_mode=1, loop_mode=0)
+    o = make_oracle(b, props, trace=True); o.step(DT, 1)
+    tr, ref = o.trace_fetch(), o.bodies()
+    assert np.isfinite(ref["v"]).all()
+    for mode in (EXACT, FAST):
+        w = gpu_world(b, props, mode); w.step(DT, 1)
+        got = w.download()
+        assert pair_list(w.debug_fetch_pairs(0)) == pair_list(tr["collisions"])
+        assert pair_list(w.debug_fetch_pairs(1)) == pair_list(tr["touches"])
+        assert (got["T"] == ref["T"]).all() and np.isfinite(got["v"]).all()
+        w.close()
+
+
+def test_decision_boundaries_dense_sweep():
+    """Thousands of pairs placed within a few ulp of d == R and |d - R| == 5e6: FAST decisions must equal the oracle's."""
+    rng = np.random.default_rng(5)
+    n = 2048
+    b = synth.random_cloud(n, seed=13)
+    b["p"][:, 0] = (np.arange(n) // 2) * 1e10               # well separated couples
+    b["p"][:, 1] = 0
+    R = (b["r"][0::2] + b["r"][1::2]).astype(np.float32)
+    target = np.where(np.arange(n // 2) % 2 == 0, R, R - np.float32(5e6)).astype(np.float32)
+    ulps = rng.integers(-3, 4, n // 2)
+    d = target.copy()
+    for k in range(3):
+        d = np.where(ulps > k, np.nextafter(d, np.float32(np.inf)), d)
+        d = np.where(ulps < -k, np.nextafter(d, np.float32(-np.inf)), d)
+    b["p"][1::2, 0] = b["p"][0::2, 0] + d
+    b["p"][1::2, 1] = 0
+    props = dict(friction=0.0, gravity_mode=1, gravity=6.6743e-11, interact_n2n=True, repulsion_stiffness=0.0, collision_mode=1, loop_mode=0)
+    o = make_oracle(b, props, trace=True); o.update_pairwise(DT)
+    tr = o.trace_fetch()
+    assert 100 < len(tr["collisions"]) < n and 50 < len(tr["touches"])
+    w = gpu_world(b, props, FAST); w.update_pairwise(DT)
+    assert pair_list(w.debug_fetch_pairs(0)) == pair_list(tr["collisions"])
+    assert pair_list(w.debug_fetch_pairs(1)) == pair_list(tr["touches"])
+    assert (w.download()["T"] == o.bodies()["T"]).all()
+
+
+def test_snapshot_14k_world_one_frame():
+    s = load_golden("snapshot_4_14k.save")
+    props = props_of(s, interact_n2n=True)
+    o = make_oracle(s.bodies, props, trace=True)
+    o.step(DT, 1)
+    ref, tr = o.bodies(), o.trace_fetch()
+    w = gpu_world(s.bodies, props, EXACT); w.step(DT, 1)
+    ok, field = bodies_equal_except_color(w.download(), ref)
+    assert ok, field
+    w.close()
+    w = gpu_world(s.bodies, props, FAST); w.step(DT, 1)
+    got = w.download()
+    assert pair_list(w.debug_fetch_pairs(0)) == pair_list(tr["collisions"])
+    assert pair_list(w.debug_fetch_pairs(1)) == pair_list(tr["touches"])
+    assert (got["T"] == ref["T"]).all()
+    ev = rel_err(got["v"], ref["v"])
+    assert np.median(ev) <= TOL_KICK_MEDIAN and ev.max() <= TOL_KICK_MAX
+
+
+# ---------------------------------------------------------------------------------------------- API behaviour
+def test_phase_calls_equal_step(kat1):
+    start, _ = kat1
+    props = smoke_props(start)
+    for mode in (EXACT, FAST):
+        a = gpu_world(start.bodies, props, mode, capture=0)
+        b = gpu_world(start.bodies, props, mode, capture=0)
+        a.step(DT, 3)
+        for _ in range(3):
+            b.update_intrinsic(DT); b.update_pairwise(DT); b.update_global(DT); b.sweep_expired(0)
+        assert a.download().tobytes() == b.download().tobytes()
+
+
+def test_body_table_operations(kat1):
+    start, _ = kat1
+    w = gpu_world(start.bodies, smoke_props(start), FAST, capture=0)
+    model = list(start.bodies.copy())
+    assert w.entity(7).tobytes() == model[7].tobytes()
+    w.remove_body(3); del model[3]
+    w.remove_body(len(model) - 1); del model[-1]
+    extra = synth.random_cloud(300, seed=99)[1:]
+    w.add_bodies(extra); model += list(extra)
+    idx = w.add_body(extra[0]); model.append(extra[0])
+    assert idx == len(model) - 1 == w.entity_count() - 1
+    e = w.entity(10).copy(); e["thrust"] = 0; e["v"] = [1.0, 2.0]
+    w.set_entity(10, e); model[10] = e
+    got = w.download()
+    assert got.tobytes() == np.array(model, dtype=capi.BODY_F32).tobytes()
+    xyr = w.download_render()
+    assert (xyr[:, :2] == got["p"]).all() and (xyr[:, 2] == got["r"]).all()
+    with pytest.raises(capi.OonError):
+        w.remove_body(10 ** 9)
+    with pytest.raises(capi.OonError):
+        w.set_props(gravity_mode=17)
+    o = make_oracle(got, smoke_props(start)); o.step(DT, 1)     # the edited table still steps like the oracle
+    w.math_mode = EXACT; w.step(DT, 1)
+    ok, field = bodies_equal_except_color(w.download(), o.bodies())
+    assert ok, field
+
+
+def test_double_build_records_roundtrip():
+    s = load_golden("one_body_realg_double.save")
+    from out_of_nothing_b200.world import World
+    w = World(0)
+    src = np.ascontiguousarray(s.bodies)
+    w._check(w._L.oon_upload_f64(w._h, src.ctypes.data, src.shape[0]))
+    out = np.zeros(1, snapshot.BODY_F64)
+    n = ctypes.c_uint64()
+    w._check(w._L.oon_download_f64(w._h, out.ctypes.data, 1, ctypes.byref(n)))
+    assert n.value == 1
+    for f in ("mass", "r", "density", "lifetime"):
+        assert out[f][0] == np.float32(s.bodies[f][0])
+    assert out["T"][0] == s.bodies["T"][0] and out["color"][0] == s.bodies["color"][0]
+
+
+def test_capacity_errors_are_reported(kat1):
+    start, _ = kat1
+    w = gpu_world(start.bodies, smoke_props(start), FAST, capture=4)      # far too small a capture buffer
+    w.step(DT, 1)
+    with pytest.raises(capi.OonError) as ei:
+        w.debug_fetch_pairs(0)
+    assert ei.value.code == capi.ERR_CAPACITY
+    buf = np.zeros(10, capi.BODY_F32)
+    with pytest.raises(capi.OonError):
+        w.download_ptr(buf.ctypes.data, 10)
+
+
+# ---------------------------------------------------------------------------------------------- full size (BASELINE.json sizes)
+@pytest.fixture(scope="module")
+def cloud_100k():
+    return synth.make("c4_cloud_100k")
+
+
+def test_full_size_fast_vs_exact_kernels_100k(cloud_100k):
+    """At 100k bodies the oracle would need minutes per frame.  Decisions: the EXACT kernel (bit-identical to the oracle
+    at every size the oracle can run) stands in -> identical counters, touch lists and T.  Kicks: a float64 numpy
+    restatement evaluated for 256 sampled targets against all 100k sources."""
+    bodies, cfg = cloud_100k
+    res = {}
+    for mode in (EXACT, FAST):
+        w = gpu_world(bodies, cfg["props"], mode, capture=1 << 24)
+        w.update_intrinsic(cfg["dt"]); w.update_pairwise(cfg["dt"])
+        res[mode] = (w.debug_fetch_kick(), w.download(), w.drain_events(), pair_list(w.debug_fetch_pairs(1)))
+        w.close()
+    assert res[FAST][2]["collisions"] == res[EXACT][2]["collisions"] > 1000
+    assert res[FAST][2]["touches"] == res[EXACT][2]["touches"] > 10
+    assert res[FAST][3] == res[EXACT][3]
+    assert (res[FAST][1]["T"] == res[EXACT][1]["T"]).all()
+    sample = np.unique(np.concatenate([[0, 1, 99999], np.random.default_rng(1).integers(0, 100000, 253)]))
+    truth = kick_f64_sample(bodies, cfg["props"], cfg["dt"], sample)
+    scale = np.sqrt((truth ** 2).sum(axis=1).mean())
+    err_fast = np.sqrt(((res[FAST][0][sample] - truth) ** 2).sum(axis=1)) / scale
+    err_exact = np.sqrt(((res[EXACT][0][sample] - truth) ** 2).sum(axis=1)) / scale
+    assert np.median(err_fast) <= TOL_KICK_MEDIAN and err_fast.max() <= TOL_KICK_MAX, (np.median(err_fast), err_fast.max())
+    assert np.median(err_fast) <= np.median(err_exact) + 1e-9      # tree-ordered FP32 sums beat the reference's running sum
+    print("100k kick error vs float64: fast median %.2e max %.2e | exact(reference order) median %.2e max %.2e"
+          % (np.median(err_fast), err_fast.max(), np.median(err_exact), err_exact.max()))
+
+
+def test_full_size_momentum_and_determinism_100k(cloud_100k):
+    bodies, cfg = cloud_100k
+    w = gpu_world(bodies, cfg["props"], FAST, capture=1 << 10)
+    w.update_intrinsic(cfg["dt"]); w.update_pairwise(cfg["dt"])
+    kick = w.debug_fetch_kick().astype(np.float64)
+    m = bodies["mass"].astype(np.float64)[:, None]
+    # Newton's third law holds pair by pair for the m/d law: sum of m*dv vanishes up to rounding
+    assert np.abs((m * kick).sum(axis=0)).max() <= 1e-5 * np.abs(m * kick).sum(axis=0).min()
+    w.update_global(cfg["dt"]); w.step(cfg["dt"], 2)
+    a = w.download(); w.close()
+    w2 = gpu_world(bodies, cfg["props"], FAST, capture=0)
+    w2.step(cfg["dt"], 3)
+    assert w2.download().tobytes() == a.tobytes()          # run-to-run bit-identical, with or without the trace hooks
+
+
+def test_full_size_oracle_sample_20k():
+    """Largest world the oracle finishes in seconds: one teacher-forced frame at 20k bodies."""
+    bodies, cfg = synth.make("c4_cloud_100k", n=20000)
+    o = make_oracle(bodies, cfg["props"], trace=True); o.step(cfg["dt"], 1)
+    ref, tr = o.bodies(), o.trace_fetch()
+    w = gpu_world(bodies, cfg["props"], FAST, capture=1 << 24); w.step(cfg["dt"], 1)
+    got = w.download()
+    assert pair_list(w.debug_fetch_pairs(0)) == pair_list(tr["collisions"])
+    assert pair_list(w.debug_fetch_pairs(1)) == pair_list(tr["touches"])
+    assert (got["T"] == ref["T"]).all()
+    ev, ep = rel_err(got["v"], ref["v"]), rel_err(got["p"], ref["p"])
+    assert np.median(ev) <= TOL_KICK_MEDIAN and ev.max() <= TOL_KICK_MAX and ep.max() <= pos_tol(ref, cfg["dt"])
