@@ -50,7 +50,8 @@ class Props(ctypes.Structure):
 
 
 class Events(ctypes.Structure):
-    _fields_ = [(n, ctypes.c_uint64) for n in ("steps", "collisions", "touches", "player_touches", "terminated", "removed")]
+    _fields_ = [(n, ctypes.c_uint64) for n in ("steps", "collisions", "touches", "player_touches", "terminated", "removed",
+                                                "warp_tiles", "warp_tiles_checked")]
 
 
 #: every symbol include/oon_gpu.h declares (tests check the library exports exactly these)

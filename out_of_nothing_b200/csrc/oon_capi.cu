@@ -21,7 +21,7 @@ using namespace oon;
 
 static_assert(sizeof(oon_body_f32) == 60, "oon_body_f32 must match the reference's float-build Entity");
 static_assert(sizeof(oon_body_f64) == 96, "oon_body_f64 must match the reference's double-build Entity");
-static_assert(sizeof(oon_props) == 40 && sizeof(oon_events) == 48, "ABI struct sizes");
+static_assert(sizeof(oon_props) == 40 && sizeof(oon_events) == 64, "ABI struct sizes");
 
 // ------------------------------------------------------------------------------------------------
 // NCCL through dlopen: a single-GPU world never needs the library.
@@ -78,6 +78,7 @@ struct oon_world {
     // partition of the world: rank g owns the contiguous index block [g*block, min(n_total,(g+1)*block))
     uint64_t n_total = 0;     // bodies in the whole world (host view; refreshed from the device after sweeps)
     uint32_t block = 0;       // slots per rank (multiple of TS); slots == block
+    uint32_t cblock = 0;      // bodies per canonical block (block == cblock * 8 / nranks)
     uint32_t n_local = 0;     // host view of the live local count
     bool has_mortals = false; // any body with lifetime > 0 or a non-unlimited non-positive lifetime
     float rmax = 0.f;         // >= every radius in the world
@@ -99,10 +100,21 @@ struct oon_world {
     float* xyr_dev = nullptr; size_t xyr_cap = 0;
     CaptureBuf cap{};
 
+    // slot order of the exchange buffer: inv[slot] = local body stored there
+    uint32_t* inv = nullptr; uint32_t inv_cap = 0;
+    int order_kind = 0;             // 0 = none yet, 1 = identity, 2 = Morton
+    bool order_dirty = true;        // body table changed since the order was computed
+    uint32_t order_age = 0;         // frames since the last Morton sort
+    uint32_t resort_every = 16;
+    bool morton_enabled = true;
+    void* order_temp = nullptr; size_t order_temp_bytes = 0;
+    unsigned long long* order_keys = nullptr; uint32_t* order_vals = nullptr; uint32_t* order_bounds = nullptr; uint32_t order_cap = 0;
+
     bool tiles_fresh = false;       // exchange buffer matches the SoA state
     uint64_t steps = 0;             // since last drain
     uint64_t launches = 0;
-    uint32_t chunk_target = 20000000u;
+    uint32_t canonical_chunks = 48;   // sources are split in (at most) this many chunks whatever the sharding
+    int sm_count = 148;
 
     int sticky = OON_OK;
     std::string error;
@@ -166,7 +178,13 @@ uint32_t round_up(uint64_t x, uint32_t m) { return uint32_t((x + m - 1) / m * m)
 // Lay the world out for `n_total` bodies: block size, SoA capacity, exchange buffer.  Keeps the first
 // `keep` local bodies of the current SoA.
 int layout(oon_world* w, uint64_t n_total, uint32_t keep) {
-    const uint32_t block = std::max<uint32_t>(TS, round_up((n_total + w->nranks - 1) / w->nranks, TS));
+    // Canonical blocks: 1/8 of the world each, whatever the number of GPUs; a rank owns 8/nranks of them.  (Other
+    // rank counts fall back to one block per rank: still correct, but their sums differ in the last bits from 1/2/4/8.)
+    const bool canon = (w->nranks == 1 || w->nranks == 2 || w->nranks == 4 || w->nranks == 8);
+    const uint32_t nblocks = canon ? 8u : uint32_t(w->nranks);
+    const uint32_t cblock = std::max<uint32_t>(TS, round_up((n_total + nblocks - 1) / nblocks, TS));
+    const uint32_t block = cblock * (nblocks / uint32_t(w->nranks));
+    w->cblock = cblock;
     if (uint64_t(block) * w->nranks > 0x7fffff00ull) return fail(w, OON_ERR_INVALID, "world too large: %llu bodies", (unsigned long long)n_total);
     if (block > w->soa[w->cur].cap) {
         // a single-GPU world gets head-room so that add_bodies rarely reallocates
@@ -184,11 +202,18 @@ int layout(oon_world* w, uint64_t n_total, uint32_t keep) {
     if (need_slots > w->tiles_cap_slots) {
         cudaFree(w->tiles); cudaFree(w->scratch4);
         w->tiles = nullptr; w->scratch4 = nullptr; w->tiles_cap_slots = 0;
-        int rc = dev_alloc(w, &w->tiles, need_slots * 4);
+        int rc = dev_alloc(w, &w->tiles, need_slots / TS * TILE_FLOATS);
         if (rc) return rc;
         if ((rc = dev_alloc(w, &w->scratch4, need_slots))) return rc;
         w->tiles_cap_slots = need_slots;
     }
+    if (w->soa[w->cur].cap > w->inv_cap) {
+        cudaFree(w->inv); w->inv = nullptr; w->inv_cap = 0;
+        int rc = dev_alloc(w, &w->inv, w->soa[w->cur].cap);
+        if (rc) return rc;
+        w->inv_cap = w->soa[w->cur].cap;
+    }
+    w->order_dirty = true;
     w->block = block;
     w->n_total = n_total;
     const uint64_t lo = uint64_t(w->rank) * block;
@@ -199,13 +224,17 @@ int layout(oon_world* w, uint64_t n_total, uint32_t keep) {
 
 uint32_t total_tiles(const oon_world* w) { return uint32_t(uint64_t(w->block) * w->nranks / TS); }
 
-void chunking(const oon_world* w, uint32_t& nchunks, uint32_t& tiles_per_chunk) {
+// Canonical split of the sources: depends on the world size only, never on the sharding or the launch geometry,
+// so that every target sees the same summation tree on 1, 2, 4 or 8 GPUs.
+void chunking(const oon_world* w, uint32_t& nchunks, uint32_t& chunk_tiles, uint32_t& cpc) {
     const uint32_t ntiles = total_tiles(w);
-    const uint64_t total_slots = uint64_t(ntiles) * TS;
-    uint64_t want = (w->chunk_target + total_slots - 1) / total_slots;   // depends on the world size only, never on the sharding
-    want = std::max<uint64_t>(1, std::min<uint64_t>(want, ntiles));
-    tiles_per_chunk = uint32_t((ntiles + want - 1) / want);
-    nchunks = (ntiles + tiles_per_chunk - 1) / tiles_per_chunk;
+    chunk_tiles = std::max<uint32_t>(1, (ntiles + w->canonical_chunks - 1) / w->canonical_chunks);
+    nchunks = (ntiles + chunk_tiles - 1) / chunk_tiles;
+    // launch geometry: enough CTAs for ~8 waves of 3 resident CTAs per SM, each walking `cpc` consecutive chunks
+    const uint64_t target_blocks = (uint64_t(w->block) + CTA_THREADS * 2 - 1) / (CTA_THREADS * 2);
+    const uint64_t want_ctas = uint64_t(w->sm_count) * 3 * 8;
+    uint64_t c = target_blocks * nchunks / std::max<uint64_t>(1, want_ctas);
+    cpc = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(c, nchunks)));
 }
 
 int ensure_partial(oon_world* w, uint32_t nchunks) {
@@ -244,7 +273,7 @@ StepParams step_params(const oon_world* w, float dt) {
     return sp;
 }
 
-float* tiles_local(oon_world* w) { return w->tiles + size_t(w->rank) * w->block * 4; }
+float* tiles_local(oon_world* w) { return w->tiles + size_t(w->rank) * (w->block / TS) * TILE_FLOATS; }
 
 // Timing scaffold for oon_step_profiled: class -> accumulated ms
 struct Prof {
@@ -272,16 +301,59 @@ int timed(oon_world* w, Prof* prof, int cls, F&& body) {
 int exchange(oon_world* w, Prof* prof) {
     if (w->nranks == 1) return OON_OK;
     return timed(w, prof, 2, [&](int& launched) -> int {
-        const size_t count = size_t(w->block) * 4;
+        const size_t count = size_t(w->block / TS) * TILE_FLOATS;
         NC(w, g_nccl.AllGather(tiles_local(w), w->tiles, count, ncclFloat, w->comm, w->stream));
         launched = 1;
         return OON_OK;
     });
 }
 
+// Morton order pays through box culling; with mortal bodies the sweep shifts indices every frame and a re-sort
+// per frame would cost more than it saves, so those worlds keep the identity order.
+bool wants_morton(const oon_world* w, const StepParams& sp) { return sp.n2n && !sp.exact && !w->has_mortals && w->morton_enabled; }
+
+// Make inv[] valid for the coming pack: identity for the reference-order kernels, Morton order of the current
+// positions for the FAST all-pairs kernel (refreshed every `resort_every` frames: order is a performance matter only).
+int ensure_order(oon_world* w, const StepParams& sp, Prof* prof, bool allow_refresh = true) {
+    const int kind = wants_morton(w, sp) ? 2 : 1;
+    // allow_refresh == false: between an interact and its integrate the partial sums are indexed by the current
+    // slots, so only a missing or invalidated order may be (re)built there, never an aged one.
+    const bool stale = w->order_dirty || w->order_kind == 0 ||
+                       (allow_refresh && (w->order_kind != kind || (kind == 2 && w->order_age >= w->resort_every)));
+    if (!stale) return OON_OK;
+    const uint32_t cap = w->soa[w->cur].cap;
+    if (kind == 2 && w->order_cap < cap) {
+        cudaFree(w->order_temp); cudaFree(w->order_keys); cudaFree(w->order_vals); cudaFree(w->order_bounds);
+        w->order_temp = nullptr; w->order_keys = nullptr; w->order_vals = nullptr; w->order_bounds = nullptr; w->order_cap = 0;
+        w->order_temp_bytes = order_temp_bytes(cap);
+        CU(w, cudaMalloc(&w->order_temp, w->order_temp_bytes));
+        int rc;
+        if ((rc = dev_alloc(w, &w->order_keys, size_t(2) * cap))) return rc;
+        if ((rc = dev_alloc(w, &w->order_vals, cap))) return rc;
+        if ((rc = dev_alloc(w, &w->order_bounds, 32))) return rc;
+        w->order_cap = cap;
+    }
+    int rc = timed(w, prof, 3, [&](int& launched) -> int {
+        if (kind == 2)
+            launched = launch_order_morton(w->stream, w->soa[w->cur].d, w->d_n, w->block, w->cblock, w->inv, w->order_temp, w->order_temp_bytes,
+                                           w->order_keys, w->order_vals, w->order_bounds);
+        else
+            launched = launch_order_identity(w->stream, w->inv, w->block);
+        CU(w, cudaGetLastError());
+        return OON_OK;
+    });
+    if (rc) return rc;
+    w->order_kind = kind; w->order_dirty = false; w->order_age = 0;
+    w->tiles_fresh = false;
+    return OON_OK;
+}
+
 int do_intrinsic_pack(oon_world* w, const StepParams& sp, bool intrinsic, Prof* prof) {
-    int rc = timed(w, prof, 1, [&](int& launched) -> int {
-        launched = launch_intrinsic_pack(w->stream, w->soa[w->cur].d, w->d_n, w->block, tiles_local(w), sp, intrinsic, w->counters);
+    int rc = ensure_order(w, sp, prof);
+    if (rc) return rc;
+    rc = timed(w, prof, 1, [&](int& launched) -> int {
+        launched = launch_intrinsic_pack(w->stream, w->soa[w->cur].d, w->inv, w->d_n, w->block, uint32_t(w->rank) * w->block,
+                                         tiles_local(w), sp, intrinsic, w->counters);
         CU(w, cudaGetLastError());
         return OON_OK;
     });
@@ -293,18 +365,18 @@ int do_intrinsic_pack(oon_world* w, const StepParams& sp, bool intrinsic, Prof* 
 }
 
 int do_interact(oon_world* w, const StepParams& sp, uint32_t& nchunks_out, Prof* prof) {
-    uint32_t nchunks = 1, tpc = total_tiles(w);
-    if (sp.n2n && !sp.exact) chunking(w, nchunks, tpc);
+    uint32_t nchunks = 1, chunk_tiles = total_tiles(w), cpc = 1;
+    if (sp.n2n && !sp.exact) chunking(w, nchunks, chunk_tiles, cpc);
     int rc = ensure_partial(w, nchunks);
     if (rc) return rc;
     nchunks_out = nchunks;
     return timed(w, prof, 0, [&](int& launched) -> int {
         if (sp.n2n)
-            launched = launch_interact(w->stream, w->tiles, total_tiles(w), nchunks, tpc, uint32_t(w->rank) * w->block, w->block, w->d_n,
-                                       w->soa[w->cur].d, w->rmax, sp, w->partial, w->counters, w->cap);
+            launched = launch_interact(w->stream, w->tiles, total_tiles(w), chunk_tiles, nchunks, cpc, uint32_t(w->rank) * w->block, w->block,
+                                       w->d_n, w->soa[w->cur].d, uint32_t(w->rank) * w->block, sp, w->partial, w->counters, w->cap);
         else
             launched = launch_interact_player_only(w->stream, w->tiles, total_tiles(w), uint32_t(w->rank) * w->block, w->block, w->d_n,
-                                                   nullptr, w->soa[w->cur].d, sp, w->partial, w->scratch4, w->counters, w->cap);
+                                                   w->soa[w->cur].d, sp, w->partial, w->scratch4, w->counters, w->cap);
         CU(w, cudaGetLastError());
         return OON_OK;
     });
@@ -324,9 +396,11 @@ int ensure_kick(oon_world* w) {
 int do_integrate(oon_world* w, const StepParams& sp, uint32_t nchunks, bool apply_pairwise, bool do_global, bool fuse_next, Prof* prof) {
     int rc = ensure_kick(w);
     if (rc) return rc;
+    if ((rc = ensure_order(w, sp, prof, false))) return rc;
     rc = timed(w, prof, 1, [&](int& launched) -> int {
-        launched = launch_integrate(w->stream, w->soa[w->cur].d, w->d_n, w->block, w->partial, nchunks, sp, apply_pairwise, do_global,
-                                    fuse_next, tiles_local(w), (apply_pairwise && w->cap.capacity) ? w->kick : nullptr, w->counters);
+        launched = launch_integrate(w->stream, w->soa[w->cur].d, w->inv, w->d_n, w->block, uint32_t(w->rank) * w->block, w->partial, nchunks,
+                                    sp, apply_pairwise, do_global, fuse_next, tiles_local(w),
+                                    (apply_pairwise && w->cap.capacity) ? w->kick : nullptr, w->counters);
         CU(w, cudaGetLastError());
         return OON_OK;
     });
@@ -367,6 +441,7 @@ int do_sweep(oon_world* w, uint32_t player_ndx, Prof* prof) {
     if (rc) return rc;
     w->cur ^= 1;
     w->tiles_fresh = false;
+    w->order_dirty = true;          // indices shifted
     return OON_OK;
 }
 
@@ -385,19 +460,21 @@ int step_impl(oon_world* w, float dt, uint32_t nsteps, Prof* prof) {
     if (!nsteps || !w->block) { w->steps += nsteps; return OON_OK; }
     const StepParams sp = step_params(w, dt);
     const bool sweep = w->has_mortals;
-    // Frame k: intrinsic+pack -> (all-gather) -> interact -> integrate.  Without mortal bodies the
-    // integrate kernel of frame k also runs frame k+1's intrinsic+pack (one pass over the SoA, one launch).
+    // Frame k: intrinsic+pack -> (all-gather) -> interact -> integrate.  Without mortal bodies the integrate kernel of
+    // frame k also runs frame k+1's intrinsic+pack (one pass over the SoA, one launch) unless the slot order is due
+    // for a refresh.
     int rc = do_intrinsic_pack(w, sp, true, prof);
     if (rc) return rc;
     for (uint32_t k = 0; k < nsteps; ++k) {
         uint32_t nchunks = 1;
         if ((rc = do_interact(w, sp, nchunks, prof))) return rc;
-        const bool fuse = !sweep && (k + 1 < nsteps);
+        ++w->order_age;
+        const bool last = k + 1 == nsteps;
+        const bool resort_due = wants_morton(w, sp) && w->order_age >= w->resort_every;
+        const bool fuse = !sweep && !last && !resort_due;
         if ((rc = do_integrate(w, sp, nchunks, true, true, fuse, prof))) return rc;
-        if (sweep) {
-            if ((rc = do_sweep(w, 0, prof))) return rc;
-            if (k + 1 < nsteps && (rc = do_intrinsic_pack(w, sp, true, prof))) return rc;
-        }
+        if (sweep && (rc = do_sweep(w, 0, prof))) return rc;
+        if (!fuse && !last && (rc = do_intrinsic_pack(w, sp, true, prof))) return rc;
     }
     w->steps += nsteps;
     return OON_OK;
@@ -457,7 +534,10 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
     auto* w = new oon_world;
     w->device = device; w->rank = rank; w->nranks = nranks;
     oon_props_default(&w->props);
-    if (const char* e = getenv("OON_CHUNK_TARGET")) { long v = atol(e); if (v > 0) w->chunk_target = uint32_t(v); }
+    w->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("OON_CANONICAL_CHUNKS")) { long v = atol(e); if (v > 0) w->canonical_chunks = uint32_t(v); }
+    if (const char* e = getenv("OON_MORTON")) w->morton_enabled = atoi(e) != 0;
+    if (const char* e = getenv("OON_RESORT_EVERY")) { long v = atol(e); if (v > 0) w->resort_every = uint32_t(v); }
     auto bail = [&](int code) { std::string msg = w->error; oon_destroy(w); g_create_error = msg; return code; };
 #define CUB_(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { w->error = std::string(#call) + " failed: " + cudaGetErrorString(e_); return bail(OON_ERR_CUDA); } } while (0)
     CUB_(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
@@ -493,6 +573,7 @@ int oon_destroy(oon_world* w) {
     cudaFree(w->tiles); cudaFree(w->partial); cudaFree(w->scratch4); cudaFree(w->kick); cudaFree(w->d_n); cudaFree(w->d_removed_count);
     cudaFree(w->counters); cudaFree(w->sweep_temp); cudaFree(w->sweep_scratch); cudaFree(w->removed_idx); cudaFree(w->aos_dev);
     cudaFree(w->xyr_dev); cudaFree(w->cap.coll); cudaFree(w->cap.touch);
+    cudaFree(w->inv); cudaFree(w->order_temp); cudaFree(w->order_keys); cudaFree(w->order_vals); cudaFree(w->order_bounds);
     if (w->ev_start) cudaEventDestroy(w->ev_start);
     if (w->ev_stop) cudaEventDestroy(w->ev_stop);
     if (w->ev_a) cudaEventDestroy(w->ev_a);
@@ -724,6 +805,7 @@ int oon_remove_body(oon_world* w, uint64_t ndx) {
     CU(w, cudaMemcpyAsync(w->d_n, &w->n_local, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
     CU(w, cudaStreamSynchronize(w->stream));
     w->tiles_fresh = false;
+    w->order_dirty = true;
     return OON_OK;
 }
 
@@ -755,6 +837,7 @@ int oon_update_pairwise(oon_world* w, float dt) {
     if (!w->tiles_fresh && (rc = do_intrinsic_pack(w, sp, false, nullptr))) return rc;
     uint32_t nchunks = 1;
     if ((rc = do_interact(w, sp, nchunks, nullptr))) return rc;
+    ++w->order_age;
     return do_integrate(w, sp, nchunks, true, false, false, nullptr);
 }
 
@@ -786,6 +869,7 @@ int oon_drain_events(oon_world* w, oon_events* out) {
     out->steps = w->steps; w->steps = 0;
     out->collisions = c[C_COLLISIONS]; out->touches = c[C_TOUCHES]; out->player_touches = c[C_PLAYER_TOUCHES];
     out->terminated = c[C_TERMINATED]; out->removed = c[C_REMOVED];
+    out->warp_tiles = c[C_WARP_TILES]; out->warp_tiles_checked = c[C_WARP_TILES_CHECKED];
     return OON_OK;
 }
 

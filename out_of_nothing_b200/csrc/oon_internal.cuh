@@ -10,13 +10,20 @@
 namespace oon {
 
 // ---- geometry of the source exchange buffer ---------------------------------------------------
-// Sources live in "tiles" of TS bodies laid out as four contiguous arrays {x[TS], y[TS], m[TS], r[TS]}
-// (AoSoA).  One tile is one 4 KiB TMA bulk copy into shared memory and lands exactly in the
-// layout the packed-FP32 inner loop reads (two sources per 64-bit register pair).
+// Sources live in "tiles" of TS bodies laid out as five contiguous arrays
+//     x[TS], y[TS], m[TS], r[TS], id[TS]   (id = global body index, uint32 bits)
+// followed by an 8-float header {min x, min y, max x, max y of the live bodies, max live radius, -, -, -}
+// (AoSoA).  One tile is one 5152-byte TMA bulk copy into shared memory and lands exactly in the layout the
+// packed-FP32 inner loop reads (two sources per 64-bit register pair).  Slot s of the buffer holds body
+// inv[s]: in FAST all-pairs mode the slots are in Morton order of the positions, so a tile is a compact
+// patch of space and its header box lets a warp skip the collision tests of far-away tiles wholesale.
 constexpr int TS = 256;                    // bodies per tile
-constexpr int TILE_FLOATS = 4 * TS;        // floats per tile
+constexpr int TILE_HDR = 5 * TS;           // float offset of the header
+constexpr int TILE_FLOATS = 5 * TS + 8;    // floats per tile
 constexpr int TILE_BYTES = TILE_FLOATS * 4;
 constexpr int CTA_THREADS = 256;
+constexpr float BOX_EMPTY = 3.0e38f;       // |coordinate| of an empty box (finite on purpose)
+constexpr uint32_t ID_NONE = 0xffffffffu;
 
 // A dead slot (padding, or a body with lifetime == 0) is parked far away with no mass and a
 // negative radius: it attracts nothing, never collides and never comes near anything.
@@ -31,7 +38,7 @@ constexpr float LIFETIME_UNLIMITED = -1.0f;         // Entity::Unlimited, Entity
 enum : uint8_t { F_IMMUNE = 1, F_FREE_COLOR = 2, F_PLAYER = 4 };
 
 // counters kept on the device (uint64 each)
-enum { C_COLLISIONS = 0, C_TOUCHES, C_PLAYER_TOUCHES, C_TERMINATED, C_REMOVED, C_CAPTURE_COLL, C_CAPTURE_TOUCH, C_COUNT };
+enum { C_COLLISIONS = 0, C_TOUCHES, C_PLAYER_TOUCHES, C_TERMINATED, C_REMOVED, C_WARP_TILES, C_WARP_TILES_CHECKED, C_CAPTURE_COLL, C_CAPTURE_TOUCH, C_COUNT };
 
 // One step's constant parameters, passed by value to the kernels.
 struct StepParams {
@@ -68,32 +75,42 @@ struct CaptureBuf {
 
 // ---- launchers (oon_kernels.cu) ------------------------------------------------------------------
 // All take the stream to launch on and return the number of kernels launched.
+// `inv` maps a local slot of the exchange buffer to the local body stored there (identity unless sorted).
 
 // AoS (60 B records) <-> SoA
 int launch_unpack_f32(cudaStream_t st, const oon_body_f32* aos, BodySoA soa, uint32_t first, uint32_t count);
 int launch_pack_f32(cudaStream_t st, BodySoA soa, oon_body_f32* aos, uint32_t first, uint32_t count);
 
-// update_intrinsic + pack the shard's slice of the exchange buffer.  `tiles_local` points at the first
-// tile of this shard; slots in [n, slots) are written dead.
-int launch_intrinsic_pack(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint32_t slots, float* tiles_local,
-                          StepParams sp, bool do_intrinsic, unsigned long long* counters);
+// slot order: identity, or Morton order of the positions (FAST all-pairs mode)
+size_t order_temp_bytes(uint32_t slots);
+int launch_order_identity(cudaStream_t st, uint32_t* inv, uint32_t slots);
+int launch_order_morton(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint32_t slots, uint32_t cblock, uint32_t* inv,
+                        void* temp, size_t temp_bytes, unsigned long long* keys2 /* 2*slots */, uint32_t* vals_in /* slots */,
+                        uint32_t* bounds /* 8 x 4 words */);
 
-// The all-pairs pass.  tiles: whole gathered buffer (ntiles tiles).  Targets = local slots
-// [0, slots) living at global slot target_base.  partial: [nchunks][slots] float4 {ax, ay, touch_count, -}.
-int launch_interact(cudaStream_t st, const float* tiles, uint32_t ntiles, uint32_t nchunks, uint32_t tiles_per_chunk,
-                    uint32_t target_base, uint32_t slots, const uint32_t* d_n_local, BodySoA soa, float rmax,
+// update_intrinsic + pack the shard's slice of the exchange buffer (one thread per slot, one block per tile).
+// body_base = global index of local body 0.  Slots >= n are written dead.
+int launch_intrinsic_pack(cudaStream_t st, BodySoA soa, const uint32_t* inv, const uint32_t* d_n, uint32_t slots,
+                          uint32_t body_base, float* tiles_local, StepParams sp, bool do_intrinsic, unsigned long long* counters);
+
+// The all-pairs pass.  tiles: whole gathered buffer (ntiles tiles).  Targets = local slots [0, slots) living at
+// global slot target_base.  Sources are split in `nchunks` canonical chunks of `chunk_tiles` tiles (a function of
+// the world size only); one CTA walks `cpc` consecutive chunks.  partial: [nchunks][slots] float4
+// {sum x, sum y, touch visits, -} indexed by local slot.
+int launch_interact(cudaStream_t st, const float* tiles, uint32_t ntiles, uint32_t chunk_tiles, uint32_t nchunks, uint32_t cpc,
+                    uint32_t target_base, uint32_t slots, const uint32_t* d_n_local, BodySoA soa, uint32_t body_base,
                     StepParams sp, float4* partial, unsigned long long* counters, CaptureBuf cap);
 
-// interact_n2n == false: only body 0 is a source (and, in half-matrix mode, the target of everyone).
+// interact_n2n == false: only body 0 is a source (and, in half-matrix mode, the target of everyone).  Identity order.
 int launch_interact_player_only(cudaStream_t st, const float* tiles, uint32_t ntiles, uint32_t target_base,
-                                uint32_t slots, const uint32_t* d_n_local, const uint32_t* d_n_total, BodySoA soa,
+                                uint32_t slots, const uint32_t* d_n_local, BodySoA soa,
                                 StepParams sp, float4* partial, float4* scratch, unsigned long long* counters, CaptureBuf cap);
 
 // update_global (+ touch heat + kick application), optionally fused with the next step's
-// update_intrinsic + pack.  kick_out (optional) receives the velocity change of the pairwise pass.
-int launch_integrate(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint32_t slots, const float4* partial,
-                     uint32_t nchunks, StepParams sp, bool apply_pairwise, bool do_global, bool fuse_next_intrinsic,
-                     float* tiles_local, float2* kick_out, unsigned long long* counters);
+// update_intrinsic + pack.  kick_out (optional, body order) receives the velocity change of the pairwise pass.
+int launch_integrate(cudaStream_t st, BodySoA soa, const uint32_t* inv, const uint32_t* d_n, uint32_t slots, uint32_t body_base,
+                     const float4* partial, uint32_t nchunks, StepParams sp, bool apply_pairwise, bool do_global,
+                     bool fuse_next_intrinsic, float* tiles_local, float2* kick_out, unsigned long long* counters);
 
 // The caller's expired-body sweep (OON.cpp:1089-1095) as a stable device compaction from `src` into `dst`.
 // d_n is updated in place.  removed_idx (optional, capacity removed_cap) gets the indices at removal time.

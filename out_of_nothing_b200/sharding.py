@@ -10,9 +10,16 @@ from __future__ import annotations
 TS = 256  # bodies per exchange tile == oon::TS in csrc/oon_internal.cuh
 
 
+CANONICAL_BLOCKS = 8
+
+
 def block_size(n: int, nranks: int) -> int:
-    per = -(-n // nranks)
-    return max(TS, -(-per // TS) * TS)
+    """Bodies per rank.  The world is cut in 8 canonical blocks (tile-aligned) whatever the GPU count; a rank owns
+    8/nranks consecutive ones, so the slot order of the exchange buffer is the same on 1, 2, 4 and 8 GPUs."""
+    nblocks = CANONICAL_BLOCKS if nranks in (1, 2, 4, 8) else nranks
+    per = -(-n // nblocks)
+    cblock = max(TS, -(-per // TS) * TS)
+    return cblock * (nblocks // nranks)
 
 
 def shard_range(n: int, rank: int, nranks: int) -> tuple[int, int]:

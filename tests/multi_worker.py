@@ -1,0 +1,26 @@
+"""Worker of the multi-GPU parity test: one process per GPU, one shard each (launched by test_gpu_multi.py)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def run(rank, nranks, nccl_id, bodies_path, out_path, mode, steps, dt, props):
+    from out_of_nothing_b200 import capi
+    from out_of_nothing_b200.world import World
+    bodies = np.load(bodies_path)
+    w = World(rank, rank, nranks, nccl_id)
+    w.set_props(**props)
+    w.math_mode = mode
+    w.upload(bodies)
+    w.step(dt, steps)
+    out = w.download()
+    xyr = w.download_render()
+    ev = w.drain_events()
+    np.save(out_path % rank, out)
+    np.save((out_path % rank) + ".xyr.npy", xyr)
+    np.save((out_path % rank) + ".ev.npy", np.array([ev["collisions"], ev["touches"]], np.int64))
+    w.close()

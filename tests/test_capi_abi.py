@@ -39,7 +39,7 @@ def test_record_layouts_match_the_reference_fixtures():
            [4, 8, 12, 16, 24, 32, 36, 40, 44]                                  # SURVEY.md App. A offsets
     assert [snapshot.BODY_F64.fields[f][1] for f in ("lifetime", "r", "density", "p", "v", "T", "color", "mass", "thrust")] == \
            [8, 16, 24, 32, 48, 64, 68, 72, 80]
-    assert ctypes.sizeof(capi.Props) == 40 and ctypes.sizeof(capi.Events) == 48
+    assert ctypes.sizeof(capi.Props) == 40 and ctypes.sizeof(capi.Events) == 64
 
 
 def test_props_default_are_the_reference_defaults():

@@ -1,0 +1,61 @@
+"""Sharded worlds (one process per GPU, NCCL all-gather of the exchange tiles) give the same bits as one GPU.
+
+Needs >= 2 GPUs; skipped otherwise.  Run with e.g. `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`.
+"""
+import multiprocessing as mp
+import os
+
+import numpy as np
+import pytest
+
+from helpers import load_golden, props_of
+from out_of_nothing_b200 import capi, synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def gpu_count():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def run_sharded(tmp_path, bodies, props, nranks, mode, steps, dt):
+    import multi_worker
+    bpath = str(tmp_path / "bodies.npy")
+    np.save(bpath, bodies)
+    out = str(tmp_path / ("out_%d_" % nranks)) + "%d.npy"
+    nccl_id = capi.nccl_unique_id() if nranks > 1 else None
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=multi_worker.run, args=(r, nranks, nccl_id, bpath, out, mode, steps, dt, props)) for r in range(nranks)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    return ([np.load(out % r) for r in range(nranks)], [np.load((out % r) + ".xyr.npy") for r in range(nranks)],
+            [np.load((out % r) + ".ev.npy") for r in range(nranks)])
+
+
+@pytest.mark.skipif(gpu_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("mode", [capi.MATH_FAST, capi.MATH_EXACT])
+@pytest.mark.parametrize("world", ["kat1", "cloud20k"])
+def test_two_gpus_bit_identical_to_one(tmp_path, mode, world):
+    if world == "kat1":
+        s = load_golden("kat1_start.state")
+        bodies, props, steps = s.bodies, props_of(s, friction=0.01, interact_n2n=True), 20
+    else:
+        bodies, cfg = synth.make("c4_cloud_100k", n=20000)
+        props, steps = cfg["props"], 6
+    props = {k: (int(v) if isinstance(v, bool) else v) for k, v in props.items()}
+    one, xyr1, ev1 = run_sharded(tmp_path, bodies, props, 1, mode, steps, 0.033)
+    nranks = min(gpu_count(), 8)
+    nranks = 1 << (nranks.bit_length() - 1)
+    many, xyrn, evn = run_sharded(tmp_path, bodies, props, nranks, mode, steps, 0.033)
+    for r in range(nranks):
+        assert many[r].tobytes() == one[0].tobytes(), "rank %d of %d differs from the single-GPU result" % (r, nranks)
+        assert xyrn[r].tobytes() == xyr1[0].tobytes()
+    total = sum(evn)                       # each visit is counted on exactly one rank (the target's owner)
+    assert total.tolist() == ev1[0].tolist()
