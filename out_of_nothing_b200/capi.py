@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liboon_gpu.so")
+LIB_PATH = os.environ.get("OON_GPU_LIB") or os.path.join(_HERE, "lib", "liboon_gpu.so")   # override: tuning variants only
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NCCL, ERR_NO_DEVICE, ERR_CAPACITY, ERR_UNSUPPORTED = range(7)
 GRAVITY_OFF, GRAVITY_HYPERBOLIC, GRAVITY_REALISTIC, GRAVITY_EXPERIMENTAL = range(4)

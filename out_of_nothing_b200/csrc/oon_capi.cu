@@ -231,8 +231,8 @@ void chunking(const oon_world* w, uint32_t& nchunks, uint32_t& chunk_tiles, uint
     chunk_tiles = std::max<uint32_t>(1, (ntiles + w->canonical_chunks - 1) / w->canonical_chunks);
     nchunks = (ntiles + chunk_tiles - 1) / chunk_tiles;
     // launch geometry: enough CTAs for ~8 waves of 3 resident CTAs per SM, each walking `cpc` consecutive chunks
-    const uint64_t target_blocks = (uint64_t(w->block) + CTA_THREADS * 2 - 1) / (CTA_THREADS * 2);
-    const uint64_t want_ctas = uint64_t(w->sm_count) * 3 * 8;
+    const uint64_t target_blocks = (uint64_t(w->block) + CTA_THREADS - 1) / CTA_THREADS;   // one target slot per thread
+    const uint64_t want_ctas = uint64_t(w->sm_count) * 4 * 8;
     uint64_t c = target_blocks * nchunks / std::max<uint64_t>(1, want_ctas);
     cpc = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(c, nchunks)));
 }
