@@ -105,8 +105,9 @@ struct oon_world {
     int order_kind = 0;             // 0 = none yet, 1 = identity, 2 = Morton
     bool order_dirty = true;        // body table changed since the order was computed
     uint32_t order_age = 0;         // frames since the last Morton sort
-    uint32_t resort_every = 16;
+    uint32_t resort_every = 1;
     bool morton_enabled = true;
+    uint64_t morton_min_bodies = 32768;
     void* order_temp = nullptr; size_t order_temp_bytes = 0;
     unsigned long long* order_keys = nullptr; uint32_t* order_vals = nullptr; uint32_t* order_bounds = nullptr; uint32_t order_cap = 0;
 
@@ -308,9 +309,12 @@ int exchange(oon_world* w, Prof* prof) {
     });
 }
 
-// Morton order pays through box culling; with mortal bodies the sweep shifts indices every frame and a re-sort
-// per frame would cost more than it saves, so those worlds keep the identity order.
-bool wants_morton(const oon_world* w, const StepParams& sp) { return sp.n2n && !sp.exact && !w->has_mortals && w->morton_enabled; }
+// Space-filling-curve order pays through box culling once the O(N^2) pass dwarfs the O(N) sort (a re-sort costs
+// ~0.1 ms; bodies of these worlds cross a tile's width in a few frames, so the order is refreshed every
+// `resort_every` frames, default 1).  Small worlds and worlds with mortal bodies keep the identity order.
+bool wants_morton(const oon_world* w, const StepParams& sp) {
+    return sp.n2n && !sp.exact && !w->has_mortals && w->morton_enabled && w->n_total >= w->morton_min_bodies;
+}
 
 // Make inv[] valid for the coming pack: identity for the reference-order kernels, Morton order of the current
 // positions for the FAST all-pairs kernel (refreshed every `resort_every` frames: order is a performance matter only).
@@ -537,6 +541,7 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
     w->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("OON_CANONICAL_CHUNKS")) { long v = atol(e); if (v > 0) w->canonical_chunks = uint32_t(v); }
     if (const char* e = getenv("OON_MORTON")) w->morton_enabled = atoi(e) != 0;
+    if (const char* e = getenv("OON_MORTON_MIN")) { long v = atol(e); if (v >= 0) w->morton_min_bodies = uint64_t(v); }
     if (const char* e = getenv("OON_RESORT_EVERY")) { long v = atol(e); if (v > 0) w->resort_every = uint32_t(v); }
     auto bail = [&](int code) { std::string msg = w->error; oon_destroy(w); g_create_error = msg; return code; };
 #define CUB_(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { w->error = std::string(#call) + " failed: " + cudaGetErrorString(e_); return bail(OON_ERR_CUDA); } } while (0)
