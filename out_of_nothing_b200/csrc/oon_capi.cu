@@ -334,7 +334,7 @@ int ensure_order(oon_world* w, const StepParams& sp, Prof* prof, bool allow_refr
         int rc;
         if ((rc = dev_alloc(w, &w->order_keys, size_t(2) * cap))) return rc;
         if ((rc = dev_alloc(w, &w->order_vals, cap))) return rc;
-        if ((rc = dev_alloc(w, &w->order_bounds, 32))) return rc;
+        if ((rc = dev_alloc(w, &w->order_bounds, 8 * 16))) return rc;     // 8 canonical blocks x ORDER_STAT_WORDS
         w->order_cap = cap;
     }
     int rc = timed(w, prof, 3, [&](int& launched) -> int {

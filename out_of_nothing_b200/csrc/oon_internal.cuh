@@ -15,7 +15,7 @@ namespace oon {
 // followed by an 8-float header {min x, min y, max x, max y of the live bodies, max live radius, -, -, -}
 // (AoSoA).  One tile is one 5152-byte TMA bulk copy into shared memory and lands exactly in the layout the
 // packed-FP32 inner loop reads (two sources per 64-bit register pair).  Slot s of the buffer holds body
-// inv[s]: in FAST all-pairs mode the slots are in Morton order of the positions, so a tile is a compact
+// inv[s]: in FAST all-pairs mode the slots follow a Hilbert curve through the positions, so a tile is a compact
 // patch of space and its header box lets a warp skip the collision tests of far-away tiles wholesale.
 constexpr int TS = 256;                    // bodies per tile
 constexpr int TILE_HDR = 5 * TS;           // float offset of the header
@@ -81,12 +81,12 @@ struct CaptureBuf {
 int launch_unpack_f32(cudaStream_t st, const oon_body_f32* aos, BodySoA soa, uint32_t first, uint32_t count);
 int launch_pack_f32(cudaStream_t st, BodySoA soa, oon_body_f32* aos, uint32_t first, uint32_t count);
 
-// slot order: identity, or Morton order of the positions (FAST all-pairs mode)
+// slot order: identity, or Hilbert-curve order of the positions (FAST all-pairs mode)
 size_t order_temp_bytes(uint32_t slots);
 int launch_order_identity(cudaStream_t st, uint32_t* inv, uint32_t slots);
 int launch_order_morton(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint32_t slots, uint32_t cblock, uint32_t* inv,
                         void* temp, size_t temp_bytes, unsigned long long* keys2 /* 2*slots */, uint32_t* vals_in /* slots */,
-                        uint32_t* bounds /* 8 x 4 words */);
+                        uint32_t* stats /* 8 x 16 words */);
 
 // update_intrinsic + pack the shard's slice of the exchange buffer (one thread per slot, one block per tile).
 // body_base = global index of local body 0.  Slots >= n are written dead.
