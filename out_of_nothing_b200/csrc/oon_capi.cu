@@ -9,6 +9,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <utility>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -102,6 +103,11 @@ struct oon_world {
 
     // slot order of the exchange buffer: inv[slot] = local body stored there
     uint32_t* inv = nullptr; uint32_t inv_cap = 0;
+    uint32_t* inv_next = nullptr;   // order being computed ahead on the aux stream (from the positions of the current frame)
+    cudaStream_t aux = nullptr;     // sort-ahead stream: the O(N) ordering of frame k+1 hides behind the O(N^2) pass of frame k
+    cudaEvent_t ev_main = nullptr, ev_sorted = nullptr;
+    bool next_order_pending = false;
+    bool async_sort = true;
     int order_kind = 0;             // 0 = none yet, 1 = identity, 2 = Morton
     bool order_dirty = true;        // body table changed since the order was computed
     uint32_t order_age = 0;         // frames since the last Morton sort
@@ -209,12 +215,15 @@ int layout(oon_world* w, uint64_t n_total, uint32_t keep) {
         w->tiles_cap_slots = need_slots;
     }
     if (w->soa[w->cur].cap > w->inv_cap) {
-        cudaFree(w->inv); w->inv = nullptr; w->inv_cap = 0;
+        if (w->next_order_pending) { CU(w, cudaStreamSynchronize(w->aux)); w->next_order_pending = false; }
+        cudaFree(w->inv); cudaFree(w->inv_next); w->inv = nullptr; w->inv_next = nullptr; w->inv_cap = 0;
         int rc = dev_alloc(w, &w->inv, w->soa[w->cur].cap);
         if (rc) return rc;
+        if ((rc = dev_alloc(w, &w->inv_next, w->soa[w->cur].cap))) return rc;
         w->inv_cap = w->soa[w->cur].cap;
     }
     w->order_dirty = true;
+    w->kick_valid = false;
     w->block = block;
     w->n_total = n_total;
     const uint64_t lo = uint64_t(w->rank) * block;
@@ -232,7 +241,7 @@ void chunking(const oon_world* w, uint32_t& nchunks, uint32_t& chunk_tiles, uint
     chunk_tiles = std::max<uint32_t>(1, (ntiles + w->canonical_chunks - 1) / w->canonical_chunks);
     nchunks = (ntiles + chunk_tiles - 1) / chunk_tiles;
     // launch geometry: enough CTAs for ~8 waves of 3 resident CTAs per SM, each walking `cpc` consecutive chunks
-    const uint64_t target_blocks = (uint64_t(w->block) + CTA_THREADS - 1) / CTA_THREADS;   // one target slot per thread
+    const uint64_t target_blocks = (uint64_t(w->block) + K1_TARGETS_PER_CTA - 1) / K1_TARGETS_PER_CTA;
     const uint64_t want_ctas = uint64_t(w->sm_count) * 4 * 8;
     uint64_t c = target_blocks * nchunks / std::max<uint64_t>(1, want_ctas);
     cpc = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(c, nchunks)));
@@ -318,28 +327,49 @@ bool wants_morton(const oon_world* w, const StepParams& sp) {
 
 // Make inv[] valid for the coming pack: identity for the reference-order kernels, Morton order of the current
 // positions for the FAST all-pairs kernel (refreshed every `resort_every` frames: order is a performance matter only).
+int ensure_order_buffers(oon_world* w) {
+    const uint32_t cap = w->soa[w->cur].cap;
+    if (w->order_cap >= cap) return OON_OK;
+    if (w->next_order_pending) { CU(w, cudaStreamSynchronize(w->aux)); w->next_order_pending = false; }
+    cudaFree(w->order_temp); cudaFree(w->order_keys); cudaFree(w->order_vals); cudaFree(w->order_bounds);
+    w->order_temp = nullptr; w->order_keys = nullptr; w->order_vals = nullptr; w->order_bounds = nullptr; w->order_cap = 0;
+    w->order_temp_bytes = order_temp_bytes(cap);
+    CU(w, cudaMalloc(&w->order_temp, w->order_temp_bytes));
+    int rc;
+    if ((rc = dev_alloc(w, &w->order_keys, size_t(2) * cap))) return rc;
+    if ((rc = dev_alloc(w, &w->order_vals, cap))) return rc;
+    if ((rc = dev_alloc(w, &w->order_bounds, 8 * 16))) return rc;     // 8 canonical blocks x ORDER_STAT_WORDS
+    w->order_cap = cap;
+    return OON_OK;
+}
+
+// Make inv[] valid for the coming pack: identity for the reference-order kernels, Hilbert order of the positions for the
+// FAST all-pairs kernel of large worlds (order is a performance matter only, never a correctness one).
 int ensure_order(oon_world* w, const StepParams& sp, Prof* prof, bool allow_refresh = true) {
     const int kind = wants_morton(w, sp) ? 2 : 1;
+    // an order computed ahead on the aux stream from the previous frame's positions: adopt it
+    if (allow_refresh && kind == 2 && w->order_kind == 2 && !w->order_dirty && w->next_order_pending) {
+        CU(w, cudaStreamWaitEvent(w->stream, w->ev_sorted, 0));
+        std::swap(w->inv, w->inv_next);
+        w->next_order_pending = false;
+        w->order_age = 0;
+        w->tiles_fresh = false;
+        return OON_OK;
+    }
     // allow_refresh == false: between an interact and its integrate the partial sums are indexed by the current
     // slots, so only a missing or invalidated order may be (re)built there, never an aged one.
     const bool stale = w->order_dirty || w->order_kind == 0 ||
                        (allow_refresh && (w->order_kind != kind || (kind == 2 && w->order_age >= w->resort_every)));
     if (!stale) return OON_OK;
-    const uint32_t cap = w->soa[w->cur].cap;
-    if (kind == 2 && w->order_cap < cap) {
-        cudaFree(w->order_temp); cudaFree(w->order_keys); cudaFree(w->order_vals); cudaFree(w->order_bounds);
-        w->order_temp = nullptr; w->order_keys = nullptr; w->order_vals = nullptr; w->order_bounds = nullptr; w->order_cap = 0;
-        w->order_temp_bytes = order_temp_bytes(cap);
-        CU(w, cudaMalloc(&w->order_temp, w->order_temp_bytes));
-        int rc;
-        if ((rc = dev_alloc(w, &w->order_keys, size_t(2) * cap))) return rc;
-        if ((rc = dev_alloc(w, &w->order_vals, cap))) return rc;
-        if ((rc = dev_alloc(w, &w->order_bounds, 8 * 16))) return rc;     // 8 canonical blocks x ORDER_STAT_WORDS
-        w->order_cap = cap;
+    if (w->next_order_pending) {                       // the table changed under an order computed ahead: drop it
+        CU(w, cudaStreamWaitEvent(w->stream, w->ev_sorted, 0));
+        w->next_order_pending = false;
     }
-    int rc = timed(w, prof, 3, [&](int& launched) -> int {
+    int rc;
+    if (kind == 2 && (rc = ensure_order_buffers(w))) return rc;
+    rc = timed(w, prof, 3, [&](int& launched) -> int {
         if (kind == 2)
-            launched = launch_order_morton(w->stream, w->soa[w->cur].d, w->d_n, w->block, w->cblock, w->inv, w->order_temp, w->order_temp_bytes,
+            launched = launch_order_morton(w->stream, w->soa[w->cur].d, w->d_n, w->block, w->cblock, 0.f, nullptr, w->inv, w->order_temp, w->order_temp_bytes,
                                            w->order_keys, w->order_vals, w->order_bounds);
         else
             launched = launch_order_identity(w->stream, w->inv, w->block);
@@ -349,6 +379,25 @@ int ensure_order(oon_world* w, const StepParams& sp, Prof* prof, bool allow_refr
     if (rc) return rc;
     w->order_kind = kind; w->order_dirty = false; w->order_age = 0;
     w->tiles_fresh = false;
+    return OON_OK;
+}
+
+// Start computing the NEXT frame's order on the aux stream from the drift prediction p + v*dt of the state just packed
+// (p and v stay untouched until this frame's integrate, which waits for the sort).  Bodies of these worlds move a third
+// of a tile per frame, so an order built from this frame's positions would be useless next frame (56 % of the tiles
+// checked instead of 8 %); the prediction misses only the coming kick.  Hiding the sort behind the interact kernel
+// saves ~85 us per frame.
+int start_order_ahead(oon_world* w, const StepParams& sp) {
+    if (!w->async_sort || w->resort_every != 1 || !wants_morton(w, sp) || w->order_kind != 2 || w->next_order_pending) return OON_OK;
+    int rc = ensure_order_buffers(w);
+    if (rc) return rc;
+    CU(w, cudaEventRecord(w->ev_main, w->stream));
+    CU(w, cudaStreamWaitEvent(w->aux, w->ev_main, 0));
+    w->launches += uint64_t(launch_order_morton(w->aux, w->soa[w->cur].d, w->d_n, w->block, w->cblock, sp.dt, w->kick_valid ? w->kick : nullptr, w->inv_next, w->order_temp,
+                                                w->order_temp_bytes, w->order_keys, w->order_vals, w->order_bounds));
+    CU(w, cudaGetLastError());
+    CU(w, cudaEventRecord(w->ev_sorted, w->aux));
+    w->next_order_pending = true;
     return OON_OK;
 }
 
@@ -365,7 +414,7 @@ int do_intrinsic_pack(oon_world* w, const StepParams& sp, bool intrinsic, Prof* 
     rc = exchange(w, prof);
     if (rc) return rc;
     w->tiles_fresh = true;
-    return OON_OK;
+    return start_order_ahead(w, sp);
 }
 
 int do_interact(oon_world* w, const StepParams& sp, uint32_t& nchunks_out, Prof* prof) {
@@ -386,8 +435,12 @@ int do_interact(oon_world* w, const StepParams& sp, uint32_t& nchunks_out, Prof*
     });
 }
 
-int ensure_kick(oon_world* w) {
-    if (w->cap.capacity == 0) return OON_OK;          // kick trace rides on the debug switch
+bool wants_kick(const oon_world* w, const StepParams& sp) {   // debug trace, or input of the order prediction
+    return w->cap.capacity != 0 || (w->async_sort && w->resort_every == 1 && wants_morton(w, sp));
+}
+
+int ensure_kick(oon_world* w, const StepParams& sp) {
+    if (!wants_kick(w, sp)) return OON_OK;
     if (w->kick_cap < w->block) {
         cudaFree(w->kick); w->kick = nullptr; w->kick_cap = 0;
         int rc = dev_alloc(w, &w->kick, w->block);
@@ -398,18 +451,20 @@ int ensure_kick(oon_world* w) {
 }
 
 int do_integrate(oon_world* w, const StepParams& sp, uint32_t nchunks, bool apply_pairwise, bool do_global, bool fuse_next, Prof* prof) {
-    int rc = ensure_kick(w);
+    int rc = ensure_kick(w, sp);
     if (rc) return rc;
     if ((rc = ensure_order(w, sp, prof, false))) return rc;
+    if (w->next_order_pending && (do_global || apply_pairwise))       // the sort-ahead reads the positions this kernel rewrites
+        CU(w, cudaStreamWaitEvent(w->stream, w->ev_sorted, 0));
     rc = timed(w, prof, 1, [&](int& launched) -> int {
         launched = launch_integrate(w->stream, w->soa[w->cur].d, w->inv, w->d_n, w->block, uint32_t(w->rank) * w->block, w->partial, nchunks,
                                     sp, apply_pairwise, do_global, fuse_next, tiles_local(w),
-                                    (apply_pairwise && w->cap.capacity) ? w->kick : nullptr, w->counters);
+                                    (apply_pairwise && wants_kick(w, sp)) ? w->kick : nullptr, w->counters);
         CU(w, cudaGetLastError());
         return OON_OK;
     });
     if (rc) return rc;
-    if (apply_pairwise && w->cap.capacity) w->kick_valid = true;
+    if (apply_pairwise && wants_kick(w, sp)) w->kick_valid = true;
     if (do_global || apply_pairwise) w->tiles_fresh = false;
     if (fuse_next) { rc = exchange(w, prof); if (rc) return rc; w->tiles_fresh = true; }
     return OON_OK;
@@ -474,7 +529,7 @@ int step_impl(oon_world* w, float dt, uint32_t nsteps, Prof* prof) {
         if ((rc = do_interact(w, sp, nchunks, prof))) return rc;
         ++w->order_age;
         const bool last = k + 1 == nsteps;
-        const bool resort_due = wants_morton(w, sp) && w->order_age >= w->resort_every;
+        const bool resort_due = wants_morton(w, sp) && (w->order_age >= w->resort_every || w->next_order_pending);
         const bool fuse = !sweep && !last && !resort_due;
         if ((rc = do_integrate(w, sp, nchunks, true, true, fuse, prof))) return rc;
         if (sweep && (rc = do_sweep(w, 0, prof))) return rc;
@@ -541,6 +596,7 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
     w->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("OON_CANONICAL_CHUNKS")) { long v = atol(e); if (v > 0) w->canonical_chunks = uint32_t(v); }
     if (const char* e = getenv("OON_MORTON")) w->morton_enabled = atoi(e) != 0;
+    if (const char* e = getenv("OON_ASYNC_SORT")) w->async_sort = atoi(e) != 0;
     if (const char* e = getenv("OON_MORTON_MIN")) { long v = atol(e); if (v >= 0) w->morton_min_bodies = uint64_t(v); }
     if (const char* e = getenv("OON_RESORT_EVERY")) { long v = atol(e); if (v > 0) w->resort_every = uint32_t(v); }
     auto bail = [&](int code) { std::string msg = w->error; oon_destroy(w); g_create_error = msg; return code; };
@@ -548,6 +604,12 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
     CUB_(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     CUB_(cudaEventCreate(&w->ev_start)); CUB_(cudaEventCreate(&w->ev_stop));
     CUB_(cudaEventCreate(&w->ev_a)); CUB_(cudaEventCreate(&w->ev_b));
+    {
+        int lo = 0, hi = 0;
+        CUB_(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUB_(cudaStreamCreateWithPriority(&w->aux, cudaStreamNonBlocking, hi));   // small kernels: let them cut in front
+    }
+    CUB_(cudaEventCreateWithFlags(&w->ev_main, cudaEventDisableTiming)); CUB_(cudaEventCreateWithFlags(&w->ev_sorted, cudaEventDisableTiming));
     CUB_(cudaMalloc(&w->d_n, sizeof(uint32_t))); CUB_(cudaMemset(w->d_n, 0, sizeof(uint32_t)));
     CUB_(cudaMalloc(&w->d_removed_count, sizeof(uint32_t))); CUB_(cudaMemset(w->d_removed_count, 0, sizeof(uint32_t)));
     CUB_(cudaMalloc(&w->counters, sizeof(unsigned long long) * C_COUNT));
@@ -573,6 +635,10 @@ int oon_destroy(oon_world* w) {
     if (!w) return OON_ERR_INVALID;
     cudaSetDevice(w->device);
     if (w->stream) cudaStreamSynchronize(w->stream);
+    if (w->aux) { cudaStreamSynchronize(w->aux); cudaStreamDestroy(w->aux); }
+    if (w->ev_main) cudaEventDestroy(w->ev_main);
+    if (w->ev_sorted) cudaEventDestroy(w->ev_sorted);
+    cudaFree(w->inv_next);
     if (w->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(w->comm);
     soa_free(w->soa[0]); soa_free(w->soa[1]);
     cudaFree(w->tiles); cudaFree(w->partial); cudaFree(w->scratch4); cudaFree(w->kick); cudaFree(w->d_n); cudaFree(w->d_removed_count);

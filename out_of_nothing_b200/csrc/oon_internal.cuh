@@ -22,6 +22,13 @@ constexpr int TILE_HDR = 5 * TS;           // float offset of the header
 constexpr int TILE_FLOATS = 5 * TS + 8;    // floats per tile
 constexpr int TILE_BYTES = TILE_FLOATS * 4;
 constexpr int CTA_THREADS = 256;
+#ifndef OON_K1_THREADS
+#define OON_K1_THREADS 256
+#endif
+#ifndef OON_K1_T
+#define OON_K1_T 1
+#endif
+constexpr int K1_TARGETS_PER_CTA = OON_K1_THREADS * OON_K1_T;   // target slots per CTA of the FAST interact kernel
 constexpr float BOX_EMPTY = 3.0e38f;       // |coordinate| of an empty box (finite on purpose)
 constexpr uint32_t ID_NONE = 0xffffffffu;
 
@@ -84,8 +91,8 @@ int launch_pack_f32(cudaStream_t st, BodySoA soa, oon_body_f32* aos, uint32_t fi
 // slot order: identity, or Hilbert-curve order of the positions (FAST all-pairs mode)
 size_t order_temp_bytes(uint32_t slots);
 int launch_order_identity(cudaStream_t st, uint32_t* inv, uint32_t slots);
-int launch_order_morton(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint32_t slots, uint32_t cblock, uint32_t* inv,
-                        void* temp, size_t temp_bytes, unsigned long long* keys2 /* 2*slots */, uint32_t* vals_in /* slots */,
+int launch_order_morton(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint32_t slots, uint32_t cblock, float predict_dt,
+                        const float2* last_kick, uint32_t* inv, void* temp, size_t temp_bytes, unsigned long long* keys2 /* 2*slots */, uint32_t* vals_in /* slots */,
                         uint32_t* stats /* 8 x 16 words */);
 
 // update_intrinsic + pack the shard's slice of the exchange buffer (one thread per slot, one block per tile).

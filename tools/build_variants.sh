@@ -6,4 +6,3 @@ rm -rf ../lib/variants; mkdir -p ../lib/variants
 build() { name=$1; shift; nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC "$@" -shared -o ../lib/variants/$name.so oon_kernels.cu oon_capi.cu -ldl & }
 build default
 wait
-ls ../lib/variants | tr '\n' ' '
