@@ -194,29 +194,23 @@ def main():
     # ---- live FP32 peak (roofline denominator) before the run, on this device
     fp32_peak = capi.measure_fp32_peak(local_rank)
 
-    flush = None
-    if not args.no_l2_flush:
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+    flush_bytes = 0 if args.no_l2_flush else (256 << 20)     # > 126 MB L2, written on the library's stream before every timed frame
 
-    # ---- warm-up
+    # ---- warm-up (the clock sampler starts here so that short timed regions still get samples under load)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     w.step(dt, max(args.warmup, 3))
     w.synchronize()
     n_start = w.entity_count()
 
     # ---- timed region: device time of exactly K frames, barrier + synchronize on both sides, max over ranks
-    sampler = ClockSampler(local_rank)
     barrier()
     launches0 = w.launch_count()
-    sampler.start()
     t_host0 = time.perf_counter()
-    if flush is None:
+    if flush_bytes == 0:
         w.timer_start(); w.step(dt, args.steps); ms = w.timer_stop()
     else:
-        ms = 0.0
-        for _ in range(args.steps):
-            flush.fill_(1)
-            torch.cuda.synchronize()                      # the flush runs on torch's stream, the frame on the library's
-            w.timer_start(); w.step(dt, 1); ms += w.timer_stop()
+        ms = w.bench_frames(dt, args.steps, flush_bytes)
     barrier()
     host_s = time.perf_counter() - t_host0
     clocks = sampler.stop()
@@ -288,8 +282,8 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "n_bodies": n, "n_bodies_end": n_end, "dt": dt, "math": args.math,
                        "parallelism": "targets sharded in %d contiguous blocks, sources all-gathered per frame (NCCL)" % world_size if world_size > 1 else "single GPU",
-                       "l2": ("flushed between timed frames (256 MiB write)" if flush is not None else
-                              "not flushed; frames timed back to back"), **cfg["props"]},
+                       "l2": ("flushed before every timed frame (256 MiB device memset on the same stream, outside the per-frame event pairs)"
+                              if flush_bytes else "not flushed; frames timed back to back"), **cfg["props"]},
             "roofline": {"bound": "fp32", "kernel": "k_interact_fast" if args.math == "fast" else "k_interact_exact",
                          "achieved": k1_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": k1_tflops / fp32_peak if fp32_peak else None, "traffic": traffic,

@@ -222,8 +222,10 @@ int layout(oon_world* w, uint64_t n_total, uint32_t keep) {
         if ((rc = dev_alloc(w, &w->inv_next, w->soa[w->cur].cap))) return rc;
         w->inv_cap = w->soa[w->cur].cap;
     }
-    w->order_dirty = true;
-    w->kick_valid = false;
+    if (block != w->block || n_total != w->n_total) {   // same table shape: a stale order is still a valid (if less tight) order
+        w->order_dirty = true;
+        w->kick_valid = false;
+    }
     w->block = block;
     w->n_total = n_total;
     const uint64_t lo = uint64_t(w->rank) * block;
@@ -539,6 +541,12 @@ int step_impl(oon_world* w, float dt, uint32_t nsteps, Prof* prof) {
     return OON_OK;
 }
 
+// Host-side edits of the body table must not race with an order being computed ahead on the aux stream.
+int quiesce_aux(oon_world* w) {
+    if (w->next_order_pending) CU(w, cudaStreamWaitEvent(w->stream, w->ev_sorted, 0));
+    return OON_OK;
+}
+
 bool mortal(float lifetime) { return lifetime > 0.f || (lifetime != LIFETIME_UNLIMITED && lifetime <= 0.f); }
 
 }  // namespace
@@ -683,6 +691,7 @@ int oon_get_math_mode(const oon_world* w, int* mode) {
 
 int oon_upload(oon_world* w, const oon_body_f32* bodies, uint64_t n) {
     CHECK_W(w);
+    { int qrc = quiesce_aux(w); if (qrc) return qrc; }
     if (n && !bodies) return fail(w, OON_ERR_INVALID, "null body table");
     bool mortals = false; float rmax = 0.f;
     for (uint64_t i = 0; i < n; ++i) { mortals |= mortal(bodies[i].lifetime); rmax = std::max(rmax, bodies[i].r); }
@@ -700,7 +709,6 @@ int oon_upload(oon_world* w, const oon_body_f32* bodies, uint64_t n) {
     CU(w, cudaMemcpyAsync(w->d_n, &w->n_local, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
     CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));
     CU(w, cudaStreamSynchronize(w->stream));     // the caller may reuse `bodies` immediately (pageable memory)
-    w->kick_valid = false;
     return OON_OK;
 }
 
@@ -806,6 +814,7 @@ int oon_body_count(oon_world* w, uint64_t* n_out) {
 
 int oon_add_bodies(oon_world* w, const oon_body_f32* bodies, uint64_t k) {
     CHECK_W(w);
+    { int qrc = quiesce_aux(w); if (qrc) return qrc; }
     if (!k) return OON_OK;
     if (!bodies) return fail(w, OON_ERR_INVALID, "null body table");
     if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "add_bodies on a sharded world: re-upload the table instead");
@@ -840,6 +849,7 @@ int oon_get_body(oon_world* w, uint64_t ndx, oon_body_f32* out) {
 
 int oon_set_body(oon_world* w, uint64_t ndx, const oon_body_f32* in) {
     CHECK_W(w);
+    { int qrc = quiesce_aux(w); if (qrc) return qrc; }
     if (!in) return fail(w, OON_ERR_INVALID, "null input");
     int rc = sync_count(w);
     if (rc) return rc;
@@ -857,6 +867,7 @@ int oon_set_body(oon_world* w, uint64_t ndx, const oon_body_f32* in) {
 
 int oon_remove_body(oon_world* w, uint64_t ndx) {
     CHECK_W(w);
+    { int qrc = quiesce_aux(w); if (qrc) return qrc; }
     int rc = sync_count(w);
     if (rc) return rc;
     if (ndx >= w->n_total) return fail(w, OON_ERR_INVALID, "body index %llu out of range (%llu bodies)", (unsigned long long)ndx, (unsigned long long)w->n_total);
@@ -956,6 +967,35 @@ int oon_timer_stop(oon_world* w, float* elapsed_ms) {
     CU(w, cudaEventSynchronize(w->ev_stop));
     CU(w, cudaEventElapsedTime(elapsed_ms, w->ev_start, w->ev_stop));
     return OON_OK;
+}
+
+int oon_bench_frames(oon_world* w, float dt, uint32_t nsteps, uint64_t flush_bytes, double* ms_sum) {
+    CHECK_W(w);
+    if (!ms_sum) return fail(w, OON_ERR_INVALID, "null output");
+    *ms_sum = 0.0;
+    if (!nsteps) return OON_OK;
+    void* flush = nullptr;
+    if (flush_bytes) CU(w, cudaMalloc(&flush, flush_bytes));
+    std::vector<cudaEvent_t> ev(size_t(2) * nsteps, nullptr);
+    int rc = OON_OK;
+    for (auto& e : ev) if (cudaEventCreate(&e) != cudaSuccess) { rc = fail(w, OON_ERR_CUDA, "cudaEventCreate failed"); break; }
+    for (uint32_t k = 0; k < nsteps && rc == OON_OK; ++k) {
+        if (flush && cudaMemsetAsync(flush, int(k & 0xff), flush_bytes, w->stream) != cudaSuccess) { rc = fail(w, OON_ERR_CUDA, "flush memset failed"); break; }
+        if (cudaEventRecord(ev[2 * k], w->stream) != cudaSuccess) { rc = fail(w, OON_ERR_CUDA, "cudaEventRecord failed"); break; }
+        rc = step_impl(w, dt, 1, nullptr);
+        if (rc == OON_OK && cudaEventRecord(ev[2 * k + 1], w->stream) != cudaSuccess) rc = fail(w, OON_ERR_CUDA, "cudaEventRecord failed");
+    }
+    if (rc == OON_OK && cudaStreamSynchronize(w->stream) != cudaSuccess) rc = fail(w, OON_ERR_CUDA, "synchronize failed");
+    if (rc == OON_OK) {
+        for (uint32_t k = 0; k < nsteps; ++k) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ev[2 * k], ev[2 * k + 1]) != cudaSuccess) { rc = fail(w, OON_ERR_CUDA, "cudaEventElapsedTime failed"); break; }
+            *ms_sum += double(ms);
+        }
+    }
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (flush) cudaFree(flush);
+    return rc;
 }
 
 int oon_launch_count(const oon_world* w, uint64_t* n_out) {

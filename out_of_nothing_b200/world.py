@@ -181,6 +181,12 @@ class World:
         names = ("interact", "integrate", "exchange", "sweep")
         return {k: float(ms[i]) for i, k in enumerate(names)}, {k: int(launches[i]) for i, k in enumerate(names)}
 
+    def bench_frames(self, dt: float, nsteps: int, flush_bytes: int = 0) -> float:
+        """nsteps frames, L2 flushed by a device memset before each, only the frames timed (CUDA events); -> total ms."""
+        ms = ctypes.c_double()
+        self._check(self._L.oon_bench_frames(self._h, dt, nsteps, flush_bytes, ctypes.byref(ms)))
+        return ms.value
+
     def synchronize(self): self._check(self._L.oon_synchronize(self._h))
 
     def drain_events(self) -> dict:
