@@ -82,11 +82,10 @@ struct oon_world {
     uint32_t cblock = 0;      // bodies per canonical block (block == cblock * 8 / nranks)
     uint32_t n_local = 0;     // host view of the live local count
     bool has_mortals = false; // any body with lifetime > 0 or a non-unlimited non-positive lifetime
-    float rmax = 0.f;         // >= every radius in the world
 
     SoAStorage soa[2];        // [cur] is live; the other one is the sweep target
     int cur = 0;
-    float* tiles = nullptr;   // [nranks*block/TS][4][TS] exchange buffer
+    float* tiles = nullptr;   // exchange buffer: nranks*block/TS tiles of TILE_FLOATS floats (x,y,m,r,id arrays + header)
     float4* partial = nullptr; size_t partial_cap = 0;   // [nchunks][block]
     float4* scratch4 = nullptr;                          // player-only reaction buffer, one float4 per slot
     size_t tiles_cap_slots = 0;                          // slots the exchange buffer (and scratch4) can hold
@@ -108,9 +107,9 @@ struct oon_world {
     cudaEvent_t ev_main = nullptr, ev_sorted = nullptr;
     bool next_order_pending = false;
     bool async_sort = true;
-    int order_kind = 0;             // 0 = none yet, 1 = identity, 2 = Morton
+    int order_kind = 0;             // 0 = none yet, 1 = identity, 2 = Hilbert curve (the code says "morton" for historical reasons)
     bool order_dirty = true;        // body table changed since the order was computed
-    uint32_t order_age = 0;         // frames since the last Morton sort
+    uint32_t order_age = 0;         // frames since the last curve sort
     uint32_t resort_every = 1;
     bool morton_enabled = true;
     uint64_t morton_min_bodies = 32768;
@@ -242,7 +241,7 @@ void chunking(const oon_world* w, uint32_t& nchunks, uint32_t& chunk_tiles, uint
     const uint32_t ntiles = total_tiles(w);
     chunk_tiles = std::max<uint32_t>(1, (ntiles + w->canonical_chunks - 1) / w->canonical_chunks);
     nchunks = (ntiles + chunk_tiles - 1) / chunk_tiles;
-    // launch geometry: enough CTAs for ~8 waves of 3 resident CTAs per SM, each walking `cpc` consecutive chunks
+    // launch geometry: enough CTAs for ~8 waves of 4 resident CTAs per SM, each walking `cpc` consecutive chunks
     const uint64_t target_blocks = (uint64_t(w->block) + K1_TARGETS_PER_CTA - 1) / K1_TARGETS_PER_CTA;
     const uint64_t want_ctas = uint64_t(w->sm_count) * 4 * 8;
     uint64_t c = target_blocks * nchunks / std::max<uint64_t>(1, want_ctas);
@@ -693,12 +692,12 @@ int oon_upload(oon_world* w, const oon_body_f32* bodies, uint64_t n) {
     CHECK_W(w);
     { int qrc = quiesce_aux(w); if (qrc) return qrc; }
     if (n && !bodies) return fail(w, OON_ERR_INVALID, "null body table");
-    bool mortals = false; float rmax = 0.f;
-    for (uint64_t i = 0; i < n; ++i) { mortals |= mortal(bodies[i].lifetime); rmax = std::max(rmax, bodies[i].r); }
+    bool mortals = false;
+    for (uint64_t i = 0; i < n; ++i) mortals |= mortal(bodies[i].lifetime);
     if (mortals && w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "bodies with finite lifetimes on a sharded world are not implemented in this build");
     int rc = layout(w, n, 0);
     if (rc) return rc;
-    w->has_mortals = mortals; w->rmax = rmax;
+    w->has_mortals = mortals;
     const uint64_t lo = uint64_t(w->rank) * w->block;
     if (w->n_local) {
         if ((rc = ensure_aos(w, w->n_local))) return rc;
@@ -823,7 +822,7 @@ int oon_add_bodies(oon_world* w, const oon_body_f32* bodies, uint64_t k) {
     const uint32_t old_n = w->n_local;
     if ((rc = layout(w, uint64_t(old_n) + k, old_n))) return rc;
     if ((rc = ensure_aos(w, k))) return rc;
-    for (uint64_t i = 0; i < k; ++i) { w->has_mortals |= mortal(bodies[i].lifetime); w->rmax = std::max(w->rmax, bodies[i].r); }
+    for (uint64_t i = 0; i < k; ++i) w->has_mortals |= mortal(bodies[i].lifetime);
     CU(w, cudaMemcpyAsync(w->aos_dev, bodies, size_t(k) * sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
     w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, old_n, uint32_t(k));
     CU(w, cudaGetLastError());
@@ -856,7 +855,7 @@ int oon_set_body(oon_world* w, uint64_t ndx, const oon_body_f32* in) {
     if (ndx >= w->n_total) return fail(w, OON_ERR_INVALID, "body index %llu out of range (%llu bodies)", (unsigned long long)ndx, (unsigned long long)w->n_total);
     if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "set_body on a sharded world: re-upload the table instead");
     if ((rc = ensure_aos(w, 1))) return rc;
-    w->has_mortals |= mortal(in->lifetime); w->rmax = std::max(w->rmax, in->r);
+    w->has_mortals |= mortal(in->lifetime);
     CU(w, cudaMemcpyAsync(w->aos_dev, in, sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
     w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, uint32_t(ndx), 1);
     CU(w, cudaGetLastError());

@@ -41,13 +41,20 @@ def run_sharded(tmp_path, bodies, props, nranks, mode, steps, dt):
 
 @pytest.mark.skipif(gpu_count() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("mode", [capi.MATH_FAST, capi.MATH_EXACT])
-@pytest.mark.parametrize("world", ["kat1", "cloud20k"])
+@pytest.mark.parametrize("world", ["kat1", "cloud20k", "cloud50k", "player_only"])
 def test_two_gpus_bit_identical_to_one(tmp_path, mode, world):
     if world == "kat1":
         s = load_golden("kat1_start.state")
         bodies, props, steps = s.bodies, props_of(s, friction=0.01, interact_n2n=True), 20
+    elif world == "player_only":                       # interact_n2n = false: body 0 (rank 0) reacts to everyone
+        s = load_golden("kat2_start.state")
+        bodies = s.bodies.copy(); bodies["gravity_immunity"][0] = 0
+        props, steps = props_of(s, friction=0.01), 10
     else:
-        bodies, cfg = synth.make("c4_cloud_100k", n=20000)
+        n = 20000 if world == "cloud20k" else 50000    # 50k: above the curve-order threshold (sort-ahead stream active)
+        if n == 50000 and mode == capi.MATH_EXACT:
+            pytest.skip("EXACT at 50k adds nothing over 20k")
+        bodies, cfg = synth.make("c4_cloud_100k", n=n)
         props, steps = cfg["props"], 6
     props = {k: (int(v) if isinstance(v, bool) else v) for k, v in props.items()}
     one, xyr1, ev1 = run_sharded(tmp_path, bodies, props, 1, mode, steps, 0.033)
