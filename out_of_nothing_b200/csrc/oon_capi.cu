@@ -121,6 +121,7 @@ struct oon_world {
     uint64_t launches = 0;
     uint32_t canonical_chunks = 48;   // sources are split in (at most) this many chunks whatever the sharding
     int sm_count = 148;
+    uint32_t debug_cpc = 0;
 
     int sticky = OON_OK;
     std::string error;
@@ -246,6 +247,7 @@ void chunking(const oon_world* w, uint32_t& nchunks, uint32_t& chunk_tiles, uint
     const uint64_t want_ctas = uint64_t(w->sm_count) * 4 * 8;
     uint64_t c = target_blocks * nchunks / std::max<uint64_t>(1, want_ctas);
     cpc = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(c, nchunks)));
+    if (w->debug_cpc) cpc = std::min<uint32_t>(w->debug_cpc, nchunks);     // tuning experiments only
 }
 
 int ensure_partial(oon_world* w, uint32_t nchunks) {
@@ -603,6 +605,7 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
     w->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("OON_CANONICAL_CHUNKS")) { long v = atol(e); if (v > 0) w->canonical_chunks = uint32_t(v); }
     if (const char* e = getenv("OON_MORTON")) w->morton_enabled = atoi(e) != 0;
+    if (const char* e = getenv("OON_DEBUG_CPC")) w->debug_cpc = uint32_t(atoi(e));
     if (const char* e = getenv("OON_ASYNC_SORT")) w->async_sort = atoi(e) != 0;
     if (const char* e = getenv("OON_MORTON_MIN")) { long v = atol(e); if (v >= 0) w->morton_min_bodies = uint64_t(v); }
     if (const char* e = getenv("OON_RESORT_EVERY")) { long v = atol(e); if (v > 0) w->resort_every = uint32_t(v); }
