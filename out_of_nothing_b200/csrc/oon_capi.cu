@@ -85,8 +85,27 @@ struct oon_world {
 
     SoAStorage soa[2];        // [cur] is live; the other one is the sweep target
     int cur = 0;
-    float* tiles = nullptr;   // exchange buffer: nranks*block/TS tiles of TILE_FLOATS floats (x,y,m,r,id arrays + header)
-    float4* partial = nullptr; size_t partial_cap = 0;   // [nchunks][block]
+    float* tiles = nullptr;   // exchange buffer in use: nranks*block/TS tiles of TILE_FLOATS floats (x,y,m,r,id arrays + header)
+    float* tiles_buf[2] = {nullptr, nullptr};            // [1] only with the peer-to-peer exchange (epoch parity picks the buffer)
+    float4* partial = nullptr; size_t partial_cap = 0;   // [block]: result of the EXACT / player-only kernels
+    unsigned long long* acc = nullptr;                   // [2][FX_LIMBS][block] exact kick sums of the FAST all-pairs kernel
+    uint32_t* touch = nullptr;                           // [block] touch visits of the FAST all-pairs kernel
+    uint32_t acc_cap = 0; bool acc_dirty = false;
+    int* fx_scale = nullptr;                             // exponent of the fixed-point sums of the last pass
+    uint32_t* rank_stats = nullptr;                      // pack kernels: {max |coord|, min |mass|, ticket}
+
+    // peer-to-peer exchange (sharded worlds on one NVLink node): the pack kernel stores this rank's slice straight into
+    // every peer's exchange buffer and raises a flag there; the interact kernel waits for the flag of a slice before
+    // the TMA of its first tile.  No collective call, no extra launch on the critical path.
+    bool p2p_wanted = true, p2p = false;
+    uint32_t epoch = 0;                                  // packs so far; slice g of buffer epoch&1 is valid once flags[g] >= epoch
+    uint32_t waited_epoch = 0;                           // last epoch a kernel of this stream has waited for
+    uint32_t* flags = nullptr;                           // [nranks], written by the peers
+    uint32_t* timeouts = nullptr;                        // waits that gave up
+    void* ipc_stage = nullptr;                           // device staging for the handle exchange
+    float* peer_tiles[2][8] = {};                        // peers' exchange buffers (imported), indexed by rank
+    uint32_t* peer_flags[8] = {};                        // peers' flag arrays (imported)
+    uint32_t group_tiles_override = 0, debug_gpc = 0;
     float4* scratch4 = nullptr;                          // player-only reaction buffer, one float4 per slot
     size_t tiles_cap_slots = 0;                          // slots the exchange buffer (and scratch4) can hold
     float2* kick = nullptr; uint32_t kick_cap = 0; bool kick_valid = false;
@@ -119,9 +138,7 @@ struct oon_world {
     bool tiles_fresh = false;       // exchange buffer matches the SoA state
     uint64_t steps = 0;             // since last drain
     uint64_t launches = 0;
-    uint32_t canonical_chunks = 48;   // sources are split in (at most) this many chunks whatever the sharding
     int sm_count = 148;
-    uint32_t debug_cpc = 0;
 
     int sticky = OON_OK;
     std::string error;
@@ -182,6 +199,106 @@ int soa_copy(oon_world* w, SoAStorage& dst, const SoAStorage& src, uint32_t n) {
 
 uint32_t round_up(uint64_t x, uint32_t m) { return uint32_t((x + m - 1) / m * m); }
 
+// ---- peer-to-peer exchange plumbing ------------------------------------------------------------------------------
+// Host-level rendezvous of the ranks: a one-word all-gather, then wait for it.
+int barrier(oon_world* w) {
+    if (w->nranks == 1 || !w->comm) return OON_OK;
+    NC(w, g_nccl.AllGather(static_cast<char*>(w->ipc_stage) + size_t(w->rank) * 4, w->ipc_stage, 4, ncclChar, w->comm, w->stream));
+    CU(w, cudaStreamSynchronize(w->stream));
+    return OON_OK;
+}
+
+void p2p_close_tiles(oon_world* w) {
+    for (int b = 0; b < 2; ++b)
+        for (int g = 0; g < 8; ++g)
+            if (w->peer_tiles[b][g]) { cudaIpcCloseMemHandle(w->peer_tiles[b][g]); w->peer_tiles[b][g] = nullptr; }
+}
+
+struct IpcMsg {
+    cudaIpcMemHandle_t tiles[2];
+    cudaIpcMemHandle_t flags;
+    int ok;
+    int pad[15];
+};
+static_assert(sizeof(IpcMsg) == 256, "IpcMsg is one 256-byte row of the staging buffer");
+
+// Export this rank's two exchange buffers (and, once, its flag array), import everybody else's.  Every rank reaches the
+// same verdict: if any export or import fails anywhere (no peer access, different nodes, two ranks in one process...)
+// all ranks fall back to the NCCL all-gather.
+int p2p_open(oon_world* w) {
+    w->p2p = false;
+    if (w->nranks < 2 || w->nranks > 8 || !w->p2p_wanted) return OON_OK;
+    IpcMsg mine{};
+    mine.ok = 1;
+    if (cudaIpcGetMemHandle(&mine.tiles[0], w->tiles_buf[0]) != cudaSuccess || cudaIpcGetMemHandle(&mine.tiles[1], w->tiles_buf[1]) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine.flags, w->flags) != cudaSuccess) {
+        cudaGetLastError();
+        mine.ok = 0;
+    }
+    std::vector<IpcMsg> all(size_t(w->nranks));
+    auto gather = [&]() -> int {
+        IpcMsg* stage = static_cast<IpcMsg*>(w->ipc_stage);
+        CU(w, cudaMemcpyAsync(stage + w->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, w->stream));
+        NC(w, g_nccl.AllGather(stage + w->rank, stage, sizeof(IpcMsg), ncclChar, w->comm, w->stream));
+        CU(w, cudaMemcpyAsync(all.data(), stage, sizeof(IpcMsg) * size_t(w->nranks), cudaMemcpyDeviceToHost, w->stream));
+        CU(w, cudaStreamSynchronize(w->stream));
+        return OON_OK;
+    };
+    int rc = gather();
+    if (rc) return rc;
+    bool ok = true;
+    for (const IpcMsg& m : all) ok = ok && m.ok;
+    if (ok) {
+        for (int g = 0; g < w->nranks && mine.ok; ++g) {
+            if (g == w->rank) continue;
+            for (int b = 0; b < 2 && mine.ok; ++b) {
+                void* ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, all[size_t(g)].tiles[b], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+                else w->peer_tiles[b][g] = static_cast<float*>(ptr);
+            }
+            if (mine.ok && !w->peer_flags[g]) {
+                void* ptr = nullptr;
+                if (cudaIpcOpenMemHandle(&ptr, all[size_t(g)].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+                else w->peer_flags[g] = static_cast<uint32_t*>(ptr);
+            }
+        }
+    }
+    if ((rc = gather())) return rc;                        // second round: did every import work everywhere?
+    for (const IpcMsg& m : all) ok = ok && m.ok;
+    if (!ok) {
+        p2p_close_tiles(w);
+        if ((rc = barrier(w))) return rc;                  // nobody maps a buffer that is about to be freed
+        cudaFree(w->tiles_buf[1]); w->tiles_buf[1] = nullptr;
+        return OON_OK;
+    }
+    w->p2p = true;
+    return OON_OK;
+}
+
+// (Re)allocate the exchange buffer(s) for `need_slots` slots.  Collective on sharded worlds (every rank lays the
+// same world out at the same time).
+int realloc_exchange(oon_world* w, size_t need_slots) {
+    CU(w, cudaStreamSynchronize(w->stream));
+    if (w->p2p) {
+        p2p_close_tiles(w);
+        int rc = barrier(w);                               // every peer has unmapped my buffers before I free them
+        if (rc) return rc;
+        w->p2p = false;
+    }
+    cudaFree(w->tiles_buf[0]); cudaFree(w->tiles_buf[1]); cudaFree(w->scratch4);
+    w->tiles_buf[0] = w->tiles_buf[1] = w->tiles = nullptr; w->scratch4 = nullptr; w->tiles_cap_slots = 0;
+    const bool try_p2p = w->nranks >= 2 && w->nranks <= 8 && w->p2p_wanted;
+    int rc = dev_alloc(w, &w->tiles_buf[0], need_slots / TS * TILE_FLOATS);
+    if (rc) return rc;
+    if (try_p2p && (rc = dev_alloc(w, &w->tiles_buf[1], need_slots / TS * TILE_FLOATS))) return rc;
+    if ((rc = dev_alloc(w, &w->scratch4, need_slots))) return rc;
+    w->tiles = w->tiles_buf[0];
+    w->tiles_cap_slots = need_slots;
+    if (try_p2p && (rc = p2p_open(w))) return rc;
+    if (w->p2p) w->tiles = w->tiles_buf[w->epoch & 1u];
+    return OON_OK;
+}
+
 // Lay the world out for `n_total` bodies: block size, SoA capacity, exchange buffer.  Keeps the first
 // `keep` local bodies of the current SoA.
 int layout(oon_world* w, uint64_t n_total, uint32_t keep) {
@@ -192,7 +309,8 @@ int layout(oon_world* w, uint64_t n_total, uint32_t keep) {
     const uint32_t cblock = std::max<uint32_t>(TS, round_up((n_total + nblocks - 1) / nblocks, TS));
     const uint32_t block = cblock * (nblocks / uint32_t(w->nranks));
     w->cblock = cblock;
-    if (uint64_t(block) * w->nranks > 0x7fffff00ull) return fail(w, OON_ERR_INVALID, "world too large: %llu bodies", (unsigned long long)n_total);
+    if (uint64_t(block) * w->nranks > 0x40000000ull)   // 2^22 tiles: the carry-save limbs take that many addends
+        return fail(w, OON_ERR_INVALID, "world too large: %llu bodies", (unsigned long long)n_total);
     if (block > w->soa[w->cur].cap) {
         // a single-GPU world gets head-room so that add_bodies rarely reallocates
         const uint32_t cap = w->nranks == 1 ? round_up(uint64_t(block) + block / 2, TS) : block;
@@ -207,12 +325,18 @@ int layout(oon_world* w, uint64_t n_total, uint32_t keep) {
     // exchange buffer (+ the player-only reaction scratch, one float4 per slot)
     const size_t need_slots = size_t(w->nranks) * (w->nranks == 1 ? w->soa[w->cur].cap : block);
     if (need_slots > w->tiles_cap_slots) {
-        cudaFree(w->tiles); cudaFree(w->scratch4);
-        w->tiles = nullptr; w->scratch4 = nullptr; w->tiles_cap_slots = 0;
-        int rc = dev_alloc(w, &w->tiles, need_slots / TS * TILE_FLOATS);
+        int rc = realloc_exchange(w, need_slots);
         if (rc) return rc;
-        if ((rc = dev_alloc(w, &w->scratch4, need_slots))) return rc;
-        w->tiles_cap_slots = need_slots;
+    }
+    // exact accumulators of the FAST all-pairs kernel, zero between passes
+    if (w->soa[w->cur].cap > w->acc_cap) {
+        cudaFree(w->acc); cudaFree(w->touch); w->acc = nullptr; w->touch = nullptr; w->acc_cap = 0;
+        const uint32_t cap = w->soa[w->cur].cap;
+        int rc = dev_alloc(w, &w->acc, size_t(2 * FX_LIMBS) * cap);
+        if (rc) return rc;
+        if ((rc = dev_alloc(w, &w->touch, cap))) return rc;
+        w->acc_cap = cap;
+        w->acc_dirty = true;
     }
     if (w->soa[w->cur].cap > w->inv_cap) {
         if (w->next_order_pending) { CU(w, cudaStreamSynchronize(w->aux)); w->next_order_pending = false; }
@@ -236,22 +360,25 @@ int layout(oon_world* w, uint64_t n_total, uint32_t keep) {
 
 uint32_t total_tiles(const oon_world* w) { return uint32_t(uint64_t(w->block) * w->nranks / TS); }
 
-// Canonical split of the sources: depends on the world size only, never on the sharding or the launch geometry,
-// so that every target sees the same summation tree on 1, 2, 4 or 8 GPUs.
-void chunking(const oon_world* w, uint32_t& nchunks, uint32_t& chunk_tiles, uint32_t& cpc) {
+// Canonical groups of source tiles: FP32 sums inside a group, exact sums across groups.  The group size is a function
+// of the world size only (it fixes the rounding of the result); how many groups one CTA walks is launch geometry and
+// free to choose: many short CTAs balance best (measured: 4-5 tiles per CTA beats 27 on 1 GPU and 9 on a 1/8 shard),
+// very large worlds walk more groups per CTA so that the grid stays below ~64 waves.
+void grouping(const oon_world* w, uint32_t& group_tiles, uint32_t& gpc) {
     const uint32_t ntiles = total_tiles(w);
-    chunk_tiles = std::max<uint32_t>(1, (ntiles + w->canonical_chunks - 1) / w->canonical_chunks);
-    nchunks = (ntiles + chunk_tiles - 1) / chunk_tiles;
-    // launch geometry: enough CTAs for ~8 waves of 4 resident CTAs per SM, each walking `cpc` consecutive chunks
+    group_tiles = ntiles >= 128 ? 4u : ntiles >= 32 ? 2u : 1u;
+    if (w->group_tiles_override) group_tiles = w->group_tiles_override;      // experiments only: changes the rounding
+    const uint64_t ngroups = (ntiles + group_tiles - 1) / group_tiles;
     const uint64_t target_blocks = (uint64_t(w->block) + K1_TARGETS_PER_CTA - 1) / K1_TARGETS_PER_CTA;
-    const uint64_t want_ctas = uint64_t(w->sm_count) * 4 * 8;
-    uint64_t c = target_blocks * nchunks / std::max<uint64_t>(1, want_ctas);
-    cpc = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(c, nchunks)));
-    if (w->debug_cpc) cpc = std::min<uint32_t>(w->debug_cpc, nchunks);     // tuning experiments only
+    const uint64_t max_ctas = uint64_t(w->sm_count) * 4 * 64;
+    uint64_t g = (target_blocks * ngroups + max_ctas - 1) / max_ctas;
+    g = std::max<uint64_t>(g, (ngroups + 65534) / 65535);                     // gridDim.y limit
+    gpc = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(g, ngroups)));
+    if (w->debug_gpc) gpc = uint32_t(std::min<uint64_t>(w->debug_gpc, ngroups));   // tuning experiments only
 }
 
-int ensure_partial(oon_world* w, uint32_t nchunks) {
-    const size_t need = size_t(nchunks) * w->block;
+int ensure_partial(oon_world* w) {
+    const size_t need = w->block;
     if (need > w->partial_cap) {
         cudaFree(w->partial); w->partial = nullptr; w->partial_cap = 0;
         int rc = dev_alloc(w, &w->partial, need);
@@ -286,7 +413,39 @@ StepParams step_params(const oon_world* w, float dt) {
     return sp;
 }
 
-float* tiles_local(oon_world* w) { return w->tiles + size_t(w->rank) * (w->block / TS) * TILE_FLOATS; }
+float* slice_of(oon_world* w, float* buffer, int rank) { return buffer + size_t(rank) * (w->block / TS) * TILE_FLOATS; }
+
+ExchangeView xview(const oon_world* w) {
+    ExchangeView x{};
+    x.nranks = uint32_t(w->nranks); x.tiles_per_rank = w->block / TS; x.rank = uint32_t(w->rank);
+    x.epoch = w->p2p ? w->epoch : 0u; x.flags = w->flags; x.timeouts = w->timeouts;
+    return x;
+}
+
+// Open the next pack: with the peer-to-peer exchange it goes to the other buffer under the next epoch, and the buffer it
+// overwrites (epoch - 2) is free on every peer because this stream has waited for every peer's flag of epoch - 1.
+int begin_pack(oon_world* w, PackOut& out) {
+    out = PackOut{};
+    out.rank_stats = w->rank_stats;
+    if (w->p2p) {
+        if (w->waited_epoch != w->epoch) {
+            w->launches += uint64_t(launch_wait_peers(w->stream, xview(w)));
+            CU(w, cudaGetLastError());
+            w->waited_epoch = w->epoch;
+        }
+        ++w->epoch;
+        w->tiles = w->tiles_buf[w->epoch & 1u];
+        out.epoch = w->epoch;
+        for (int g = 0; g < w->nranks; ++g) {
+            if (g == w->rank) continue;
+            out.peer_tiles[out.npeers] = slice_of(w, w->peer_tiles[w->epoch & 1u][g], w->rank);
+            out.peer_flags[out.npeers] = w->peer_flags[g] + w->rank;
+            ++out.npeers;
+        }
+    }
+    out.tiles_local = slice_of(w, w->tiles, w->rank);
+    return OON_OK;
+}
 
 // Timing scaffold for oon_step_profiled: class -> accumulated ms
 struct Prof {
@@ -312,10 +471,10 @@ int timed(oon_world* w, Prof* prof, int cls, F&& body) {
 }
 
 int exchange(oon_world* w, Prof* prof) {
-    if (w->nranks == 1) return OON_OK;
+    if (w->nranks == 1 || w->p2p) return OON_OK;           // peer-to-peer: the pack kernel has already stored the slice everywhere
     return timed(w, prof, 2, [&](int& launched) -> int {
         const size_t count = size_t(w->block / TS) * TILE_FLOATS;
-        NC(w, g_nccl.AllGather(tiles_local(w), w->tiles, count, ncclFloat, w->comm, w->stream));
+        NC(w, g_nccl.AllGather(slice_of(w, w->tiles, w->rank), w->tiles, count, ncclFloat, w->comm, w->stream));
         launched = 1;
         return OON_OK;
     });
@@ -407,9 +566,11 @@ int start_order_ahead(oon_world* w, const StepParams& sp) {
 int do_intrinsic_pack(oon_world* w, const StepParams& sp, bool intrinsic, Prof* prof) {
     int rc = ensure_order(w, sp, prof);
     if (rc) return rc;
+    PackOut out;
+    if ((rc = begin_pack(w, out))) return rc;
     rc = timed(w, prof, 1, [&](int& launched) -> int {
         launched = launch_intrinsic_pack(w->stream, w->soa[w->cur].d, w->inv, w->d_n, w->block, uint32_t(w->rank) * w->block,
-                                         tiles_local(w), sp, intrinsic, w->counters);
+                                         out, sp, intrinsic, w->counters);
         CU(w, cudaGetLastError());
         return OON_OK;
     });
@@ -420,22 +581,34 @@ int do_intrinsic_pack(oon_world* w, const StepParams& sp, bool intrinsic, Prof* 
     return start_order_ahead(w, sp);
 }
 
-int do_interact(oon_world* w, const StepParams& sp, uint32_t& nchunks_out, Prof* prof) {
-    uint32_t nchunks = 1, chunk_tiles = total_tiles(w), cpc = 1;
-    if (sp.n2n && !sp.exact) chunking(w, nchunks, chunk_tiles, cpc);
-    int rc = ensure_partial(w, nchunks);
-    if (rc) return rc;
-    nchunks_out = nchunks;
-    return timed(w, prof, 0, [&](int& launched) -> int {
+int do_interact(oon_world* w, const StepParams& sp, Prof* prof) {
+    uint32_t group_tiles = 1, gpc = 1;
+    const bool fast_n2n = sp.n2n && !sp.exact;
+    int rc;
+    if (fast_n2n) {
+        grouping(w, group_tiles, gpc);
+        if (w->acc_dirty) {                                // only after a (re)allocation or a pass nobody integrated
+            CU(w, cudaMemsetAsync(w->acc, 0, sizeof(unsigned long long) * 2 * FX_LIMBS * w->acc_cap, w->stream));
+            CU(w, cudaMemsetAsync(w->touch, 0, sizeof(uint32_t) * w->acc_cap, w->stream));
+        }
+        w->acc_dirty = true;
+    } else if ((rc = ensure_partial(w))) return rc;
+    const ExchangeView xv = xview(w);
+    rc = timed(w, prof, 0, [&](int& launched) -> int {
         if (sp.n2n)
-            launched = launch_interact(w->stream, w->tiles, total_tiles(w), chunk_tiles, nchunks, cpc, uint32_t(w->rank) * w->block, w->block,
-                                       w->d_n, w->soa[w->cur].d, uint32_t(w->rank) * w->block, sp, w->partial, w->counters, w->cap);
+            launched = launch_interact(w->stream, w->tiles, total_tiles(w), group_tiles, gpc, uint32_t(w->rank) * w->block, w->block,
+                                       w->d_n, w->soa[w->cur].d, uint32_t(w->rank) * w->block, sp, xv, w->acc, w->touch, w->fx_scale, w->partial,
+                                       w->counters, w->cap);
         else
-            launched = launch_interact_player_only(w->stream, w->tiles, total_tiles(w), uint32_t(w->rank) * w->block, w->block, w->d_n,
+            launched = launch_wait_peers(w->stream, xv) +
+                       launch_interact_player_only(w->stream, w->tiles, total_tiles(w), uint32_t(w->rank) * w->block, w->block, w->d_n,
                                                    w->soa[w->cur].d, sp, w->partial, w->scratch4, w->counters, w->cap);
         CU(w, cudaGetLastError());
         return OON_OK;
     });
+    if (rc) return rc;
+    w->waited_epoch = w->epoch;                            // every kernel above waits for all the slices of this epoch
+    return OON_OK;
 }
 
 bool wants_kick(const oon_world* w, const StepParams& sp) {   // debug trace, or input of the order prediction
@@ -453,21 +626,24 @@ int ensure_kick(oon_world* w, const StepParams& sp) {
     return OON_OK;
 }
 
-int do_integrate(oon_world* w, const StepParams& sp, uint32_t nchunks, bool apply_pairwise, bool do_global, bool fuse_next, Prof* prof) {
+int do_integrate(oon_world* w, const StepParams& sp, bool apply_pairwise, bool do_global, bool fuse_next, Prof* prof) {
     int rc = ensure_kick(w, sp);
     if (rc) return rc;
     if ((rc = ensure_order(w, sp, prof, false))) return rc;
     if (w->next_order_pending && (do_global || apply_pairwise))       // the sort-ahead reads the positions this kernel rewrites
         CU(w, cudaStreamWaitEvent(w->stream, w->ev_sorted, 0));
+    PackOut out{};
+    if (fuse_next && (rc = begin_pack(w, out))) return rc;
     rc = timed(w, prof, 1, [&](int& launched) -> int {
-        launched = launch_integrate(w->stream, w->soa[w->cur].d, w->inv, w->d_n, w->block, uint32_t(w->rank) * w->block, w->partial, nchunks,
-                                    sp, apply_pairwise, do_global, fuse_next, tiles_local(w),
+        launched = launch_integrate(w->stream, w->soa[w->cur].d, w->inv, w->d_n, w->block, uint32_t(w->rank) * w->block, w->partial,
+                                    w->acc, w->touch, w->fx_scale, sp, apply_pairwise, do_global, fuse_next, out,
                                     (apply_pairwise && wants_kick(w, sp)) ? w->kick : nullptr, w->counters);
         CU(w, cudaGetLastError());
         return OON_OK;
     });
     if (rc) return rc;
     if (apply_pairwise && wants_kick(w, sp)) w->kick_valid = true;
+    if (apply_pairwise && sp.n2n && !sp.exact) w->acc_dirty = false;     // k_integrate has zeroed what it read
     if (do_global || apply_pairwise) w->tiles_fresh = false;
     if (fuse_next) { rc = exchange(w, prof); if (rc) return rc; w->tiles_fresh = true; }
     return OON_OK;
@@ -528,13 +704,12 @@ int step_impl(oon_world* w, float dt, uint32_t nsteps, Prof* prof) {
     int rc = do_intrinsic_pack(w, sp, true, prof);
     if (rc) return rc;
     for (uint32_t k = 0; k < nsteps; ++k) {
-        uint32_t nchunks = 1;
-        if ((rc = do_interact(w, sp, nchunks, prof))) return rc;
+        if ((rc = do_interact(w, sp, prof))) return rc;
         ++w->order_age;
         const bool last = k + 1 == nsteps;
         const bool resort_due = wants_morton(w, sp) && (w->order_age >= w->resort_every || w->next_order_pending);
         const bool fuse = !sweep && !last && !resort_due;
-        if ((rc = do_integrate(w, sp, nchunks, true, true, fuse, prof))) return rc;
+        if ((rc = do_integrate(w, sp, true, true, fuse, prof))) return rc;
         if (sweep && (rc = do_sweep(w, 0, prof))) return rc;
         if (!fuse && !last && (rc = do_intrinsic_pack(w, sp, true, prof))) return rc;
     }
@@ -603,9 +778,10 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
     w->device = device; w->rank = rank; w->nranks = nranks;
     oon_props_default(&w->props);
     w->sm_count = prop.multiProcessorCount;
-    if (const char* e = getenv("OON_CANONICAL_CHUNKS")) { long v = atol(e); if (v > 0) w->canonical_chunks = uint32_t(v); }
+    if (const char* e = getenv("OON_GROUP_TILES")) { long v = atol(e); if (v > 0) w->group_tiles_override = uint32_t(v); }
+    if (const char* e = getenv("OON_P2P")) w->p2p_wanted = atoi(e) != 0;
     if (const char* e = getenv("OON_MORTON")) w->morton_enabled = atoi(e) != 0;
-    if (const char* e = getenv("OON_DEBUG_CPC")) w->debug_cpc = uint32_t(atoi(e));
+    if (const char* e = getenv("OON_DEBUG_GPC")) w->debug_gpc = uint32_t(atoi(e));
     if (const char* e = getenv("OON_ASYNC_SORT")) w->async_sort = atoi(e) != 0;
     if (const char* e = getenv("OON_MORTON_MIN")) { long v = atol(e); if (v >= 0) w->morton_min_bodies = uint64_t(v); }
     if (const char* e = getenv("OON_RESORT_EVERY")) { long v = atol(e); if (v > 0) w->resort_every = uint32_t(v); }
@@ -624,6 +800,17 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
     CUB_(cudaMalloc(&w->d_removed_count, sizeof(uint32_t))); CUB_(cudaMemset(w->d_removed_count, 0, sizeof(uint32_t)));
     CUB_(cudaMalloc(&w->counters, sizeof(unsigned long long) * C_COUNT));
     CUB_(cudaMemset(w->counters, 0, sizeof(unsigned long long) * C_COUNT));
+    CUB_(cudaMalloc(&w->fx_scale, sizeof(int))); CUB_(cudaMemset(w->fx_scale, 0, sizeof(int)));
+    {
+        const uint32_t init[3] = {0u, 0x7f61b1e6u /* BOX_EMPTY */, 0u};
+        static_assert(BOX_EMPTY == 3.0e38f, "rank_stats initialiser");
+        CUB_(cudaMalloc(&w->rank_stats, sizeof init)); CUB_(cudaMemcpy(w->rank_stats, init, sizeof init, cudaMemcpyHostToDevice));
+    }
+    if (nranks > 1) {
+        CUB_(cudaMalloc(&w->flags, sizeof(uint32_t) * size_t(nranks))); CUB_(cudaMemset(w->flags, 0, sizeof(uint32_t) * size_t(nranks)));
+        CUB_(cudaMalloc(&w->timeouts, sizeof(uint32_t))); CUB_(cudaMemset(w->timeouts, 0, sizeof(uint32_t)));
+        CUB_(cudaMalloc(&w->ipc_stage, 256 * size_t(nranks)));
+    }
 #undef CUB_
     if (nranks > 1) {
         if (!id) { w->error = "sharded world needs an NCCL unique id"; return bail(OON_ERR_INVALID); }
@@ -646,12 +833,20 @@ int oon_destroy(oon_world* w) {
     cudaSetDevice(w->device);
     if (w->stream) cudaStreamSynchronize(w->stream);
     if (w->aux) { cudaStreamSynchronize(w->aux); cudaStreamDestroy(w->aux); }
+    if (w->p2p && w->sticky == OON_OK) {
+        // Collective: no kernel of any rank still stores into a peer's buffer, and nobody frees a buffer a peer still maps.
+        barrier(w);
+        p2p_close_tiles(w);
+        for (int g = 0; g < 8; ++g) if (w->peer_flags[g]) { cudaIpcCloseMemHandle(w->peer_flags[g]); w->peer_flags[g] = nullptr; }
+        barrier(w);
+    }
     if (w->ev_main) cudaEventDestroy(w->ev_main);
     if (w->ev_sorted) cudaEventDestroy(w->ev_sorted);
     cudaFree(w->inv_next);
     if (w->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(w->comm);
     soa_free(w->soa[0]); soa_free(w->soa[1]);
-    cudaFree(w->tiles); cudaFree(w->partial); cudaFree(w->scratch4); cudaFree(w->kick); cudaFree(w->d_n); cudaFree(w->d_removed_count);
+    cudaFree(w->tiles_buf[0]); cudaFree(w->tiles_buf[1]); cudaFree(w->acc); cudaFree(w->touch); cudaFree(w->fx_scale); cudaFree(w->rank_stats);
+    cudaFree(w->flags); cudaFree(w->timeouts); cudaFree(w->ipc_stage); cudaFree(w->partial); cudaFree(w->scratch4); cudaFree(w->kick); cudaFree(w->d_n); cudaFree(w->d_removed_count);
     cudaFree(w->counters); cudaFree(w->sweep_temp); cudaFree(w->sweep_scratch); cudaFree(w->removed_idx); cudaFree(w->aos_dev);
     cudaFree(w->xyr_dev); cudaFree(w->cap.coll); cudaFree(w->cap.touch);
     cudaFree(w->inv); cudaFree(w->order_temp); cudaFree(w->order_keys); cudaFree(w->order_vals); cudaFree(w->order_bounds);
@@ -919,16 +1114,15 @@ int oon_update_pairwise(oon_world* w, float dt) {
     const StepParams sp = step_params(w, dt);
     int rc;
     if (!w->tiles_fresh && (rc = do_intrinsic_pack(w, sp, false, nullptr))) return rc;
-    uint32_t nchunks = 1;
-    if ((rc = do_interact(w, sp, nchunks, nullptr))) return rc;
+    if ((rc = do_interact(w, sp, nullptr))) return rc;
     ++w->order_age;
-    return do_integrate(w, sp, nchunks, true, false, false, nullptr);
+    return do_integrate(w, sp, true, false, false, nullptr);
 }
 
 int oon_update_global(oon_world* w, float dt) {
     CHECK_W(w);
     if (!w->block) return OON_OK;
-    return do_integrate(w, step_params(w, dt), 1, false, true, false, nullptr);
+    return do_integrate(w, step_params(w, dt), false, true, false, nullptr);
 }
 
 int oon_sweep_expired(oon_world* w, uint64_t player_ndx) {

@@ -80,6 +80,39 @@ struct CaptureBuf {
     uint32_t capacity;  // 0 = capture off
 };
 
+// Where a pack kernel writes this rank's slice of the exchange tiles.
+constexpr int MAX_PEERS = 7;
+struct PackOut {
+    float* tiles_local;              // this rank's slice inside its own exchange buffer
+    uint32_t* rank_stats;            // {max |coordinate| bits, min non-zero |mass| bits, block ticket}
+    uint32_t npeers;                 // peer-to-peer exchange: remote ranks the slice is also stored to (0: NCCL all-gather / one GPU)
+    uint32_t epoch;                  // value this rank's flag is raised to once the slice has landed everywhere
+    float* peer_tiles[MAX_PEERS];    // this rank's slice inside each peer's exchange buffer (NVLink peer memory)
+    uint32_t* peer_flags[MAX_PEERS]; // this rank's flag at each peer
+};
+
+// What the FAST all-pairs kernel needs to know about the exchange.
+struct ExchangeView {
+    uint32_t nranks;                 // slices in the exchange buffer
+    uint32_t tiles_per_rank;
+    uint32_t rank;                   // own slice
+    uint32_t epoch;                  // peer-to-peer exchange: slice g may be read once flags[g] >= epoch; 0: no flags to wait for
+    const uint32_t* flags;           // [nranks], written by the peers
+    uint32_t* timeouts;              // counts waits that gave up (a peer that never arrived): sticky error on the host
+};
+
+// ---- exact accumulation of the per-group sums ---------------------------------------------------
+// The FAST all-pairs kernel sums in FP32 inside a canonical GROUP of source tiles (a function of the world size
+// only) and adds the group sums of a target in fixed point: value = (w0 + w1*2^40 + w2*2^80) * 2^B with three
+// signed 64-bit limbs per component (carry-save: limbs are summed independently with integer atomics and
+// normalised once in k_integrate).  Integer addition is associative, so the result does not depend on which
+// CTA, in which order, on which GPU handled a group: any launch geometry and any sharding give the same bits.
+// B comes from the world statistics in the tile headers; the 120-bit window leaves 2^88 for the product of the
+// mass ratio and the distance ratio of the world before the smallest addend loses FP32 precision.
+constexpr int FX_LIMB_BITS = 40;
+constexpr int FX_LIMBS = 3;
+constexpr int FX_MAX_SHIFT = 96;     // 24-bit mantissa << 96 = 120 bits
+
 // ---- launchers (oon_kernels.cu) ------------------------------------------------------------------
 // All take the stream to launch on and return the number of kernels launched.
 // `inv` maps a local slot of the exchange buffer to the local body stored there (identity unless sorted).
@@ -98,15 +131,20 @@ int launch_order_morton(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint3
 // update_intrinsic + pack the shard's slice of the exchange buffer (one thread per slot, one block per tile).
 // body_base = global index of local body 0.  Slots >= n are written dead.
 int launch_intrinsic_pack(cudaStream_t st, BodySoA soa, const uint32_t* inv, const uint32_t* d_n, uint32_t slots,
-                          uint32_t body_base, float* tiles_local, StepParams sp, bool do_intrinsic, unsigned long long* counters);
+                          uint32_t body_base, const PackOut& out, StepParams sp, bool do_intrinsic, unsigned long long* counters);
 
 // The all-pairs pass.  tiles: whole gathered buffer (ntiles tiles).  Targets = local slots [0, slots) living at
-// global slot target_base.  Sources are split in `nchunks` canonical chunks of `chunk_tiles` tiles (a function of
-// the world size only); one CTA walks `cpc` consecutive chunks.  partial: [nchunks][slots] float4
-// {sum x, sum y, touch visits, -} indexed by local slot.
-int launch_interact(cudaStream_t st, const float* tiles, uint32_t ntiles, uint32_t chunk_tiles, uint32_t nchunks, uint32_t cpc,
+// global slot target_base.  FAST: sources are cut in canonical groups of `group_tiles` tiles (a function of the
+// world size only); one CTA walks `gpc` consecutive groups (launch geometry, free); group sums go to
+// acc [2 components][FX_LIMBS][slots] (64-bit integer atomics) and touch visits to touch[slots].
+// EXACT: partial[slots] = {new v.x, new v.y, touch visits, -}.
+int launch_interact(cudaStream_t st, const float* tiles, uint32_t ntiles, uint32_t group_tiles, uint32_t gpc,
                     uint32_t target_base, uint32_t slots, const uint32_t* d_n_local, BodySoA soa, uint32_t body_base,
-                    StepParams sp, float4* partial, unsigned long long* counters, CaptureBuf cap);
+                    StepParams sp, const ExchangeView& xv, unsigned long long* acc, uint32_t* touch, int* fx_scale, float4* partial,
+                    unsigned long long* counters, CaptureBuf cap);
+// Peer-to-peer exchange: hold the stream until every peer's slice of epoch xv.epoch has landed (for the kernels that
+// read the exchange buffer without waiting themselves).
+int launch_wait_peers(cudaStream_t st, const ExchangeView& xv);
 
 // interact_n2n == false: only body 0 is a source (and, in half-matrix mode, the target of everyone).  Identity order.
 int launch_interact_player_only(cudaStream_t st, const float* tiles, uint32_t ntiles, uint32_t target_base,
@@ -115,9 +153,12 @@ int launch_interact_player_only(cudaStream_t st, const float* tiles, uint32_t nt
 
 // update_global (+ touch heat + kick application), optionally fused with the next step's
 // update_intrinsic + pack.  kick_out (optional, body order) receives the velocity change of the pairwise pass.
+// FAST all-pairs results come from acc/touch (normalised, converted and zeroed here; *fx_scale = the exponent B the
+// interact kernel used), EXACT / player-only results from partial[slots].
 int launch_integrate(cudaStream_t st, BodySoA soa, const uint32_t* inv, const uint32_t* d_n, uint32_t slots, uint32_t body_base,
-                     const float4* partial, uint32_t nchunks, StepParams sp, bool apply_pairwise, bool do_global,
-                     bool fuse_next_intrinsic, float* tiles_local, float2* kick_out, unsigned long long* counters);
+                     const float4* partial, unsigned long long* acc, uint32_t* touch, const int* fx_scale,
+                     StepParams sp, bool apply_pairwise, bool do_global,
+                     bool fuse_next_intrinsic, const PackOut& out, float2* kick_out, unsigned long long* counters);
 
 // The caller's expired-body sweep (OON.cpp:1089-1095) as a stable device compaction from `src` into `dst`.
 // d_n is updated in place.  removed_idx (optional, capacity removed_cap) gets the indices at removal time.
