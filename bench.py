@@ -281,7 +281,10 @@ def main():
             "steps_per_sec": args.steps / (ms * 1e-3),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, "n_bodies": n, "n_bodies_end": n_end, "dt": dt, "math": args.math,
-                       "parallelism": "targets sharded in %d contiguous blocks, sources all-gathered per frame (NCCL)" % world_size if world_size > 1 else "single GPU",
+                       "parallelism": ("targets sharded in %d contiguous blocks; exchange of the source tiles per frame: %s" % (
+                           world_size, {"peer_stores": "pack kernel stores each slice into every peer's buffer over NVLink (CUDA IPC), interact kernel waits on per-slice flags",
+                                        "nccl_allgather": "NCCL all-gather"}[w.exchange_kind()])) if world_size > 1 else "single GPU",
+                       "exchange": w.exchange_kind(),
                        "l2": ("flushed before every timed frame (256 MiB device memset on the same stream, outside the per-frame event pairs)"
                               if flush_bytes else "not flushed; frames timed back to back"), **cfg["props"]},
             "roofline": {"bound": "fp32", "kernel": "k_interact_fast" if args.math == "fast" else "k_interact_exact",

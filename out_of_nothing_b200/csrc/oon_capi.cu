@@ -131,6 +131,7 @@ struct oon_world {
     uint32_t order_age = 0;         // frames since the last curve sort
     uint32_t resort_every = 1;
     bool morton_enabled = true;
+    bool order_one_cta = true;      // canonical blocks that fit one CTA are ordered by one launch (k_order_block)
     uint64_t morton_min_bodies = 32768;
     void* order_temp = nullptr; size_t order_temp_bytes = 0;
     unsigned long long* order_keys = nullptr; uint32_t* order_vals = nullptr; uint32_t* order_bounds = nullptr; uint32_t order_cap = 0;
@@ -447,27 +448,47 @@ int begin_pack(oon_world* w, PackOut& out) {
     return OON_OK;
 }
 
-// Timing scaffold for oon_step_profiled: class -> accumulated ms
+// Timing scaffold for oon_step_profiled: class -> accumulated ms.  Every kernel class is bracketed by its own event
+// pair on the launching stream; nothing synchronises with the host until the call has enqueued all its frames (a host
+// round trip per kernel would let the ranks of a sharded world drift apart and put launch latency into the numbers).
 struct Prof {
     bool on = false;
     float ms[4] = {0, 0, 0, 0};
     uint32_t launches[4] = {0, 0, 0, 0};
+    struct Span { cudaEvent_t a, b; int cls; };
+    std::vector<Span> spans;
 };
 
 template <class F>
 int timed(oon_world* w, Prof* prof, int cls, F&& body) {
-    if (prof && prof->on) CU(w, cudaEventRecord(w->ev_a, w->stream));
+    Prof::Span sp{nullptr, nullptr, cls};
+    if (prof && prof->on) {
+        CU(w, cudaEventCreate(&sp.a)); CU(w, cudaEventCreate(&sp.b));
+        prof->spans.push_back(sp);
+        CU(w, cudaEventRecord(sp.a, w->stream));
+    }
     int launched = 0;
     int rc = body(launched);
     if (rc) return rc;
     w->launches += uint64_t(launched);
     if (prof && prof->on) {
-        CU(w, cudaEventRecord(w->ev_b, w->stream));
-        CU(w, cudaEventSynchronize(w->ev_b));
-        float ms = 0; CU(w, cudaEventElapsedTime(&ms, w->ev_a, w->ev_b));
-        prof->ms[cls] += ms; prof->launches[cls] += uint32_t(launched);
+        CU(w, cudaEventRecord(sp.b, w->stream));
+        prof->launches[cls] += uint32_t(launched);
     }
     return OON_OK;
+}
+
+int prof_collect(oon_world* w, Prof* prof) {
+    int rc = OON_OK;
+    if (cudaStreamSynchronize(w->stream) != cudaSuccess) rc = fail(w, OON_ERR_CUDA, "synchronize failed");
+    for (Prof::Span& sp : prof->spans) {
+        float ms = 0.f;
+        if (rc == OON_OK && cudaEventElapsedTime(&ms, sp.a, sp.b) != cudaSuccess) rc = fail(w, OON_ERR_CUDA, "cudaEventElapsedTime failed");
+        prof->ms[sp.cls] += ms;
+        cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+    }
+    prof->spans.clear();
+    return rc;
 }
 
 int exchange(oon_world* w, Prof* prof) {
@@ -530,7 +551,9 @@ int ensure_order(oon_world* w, const StepParams& sp, Prof* prof, bool allow_refr
     int rc;
     if (kind == 2 && (rc = ensure_order_buffers(w))) return rc;
     rc = timed(w, prof, 3, [&](int& launched) -> int {
-        if (kind == 2)
+        if (kind == 2 && order_fits_one_cta(w->cblock) && w->order_one_cta)
+            launched = launch_order_block(w->stream, w->soa[w->cur].d, w->d_n, w->block, w->cblock, 0.f, nullptr, w->inv);
+        else if (kind == 2)
             launched = launch_order_morton(w->stream, w->soa[w->cur].d, w->d_n, w->block, w->cblock, 0.f, nullptr, w->inv, w->order_temp, w->order_temp_bytes,
                                            w->order_keys, w->order_vals, w->order_bounds);
         else
@@ -555,8 +578,11 @@ int start_order_ahead(oon_world* w, const StepParams& sp) {
     if (rc) return rc;
     CU(w, cudaEventRecord(w->ev_main, w->stream));
     CU(w, cudaStreamWaitEvent(w->aux, w->ev_main, 0));
-    w->launches += uint64_t(launch_order_morton(w->aux, w->soa[w->cur].d, w->d_n, w->block, w->cblock, sp.dt, w->kick_valid ? w->kick : nullptr, w->inv_next, w->order_temp,
-                                                w->order_temp_bytes, w->order_keys, w->order_vals, w->order_bounds));
+    if (order_fits_one_cta(w->cblock) && w->order_one_cta)
+        w->launches += uint64_t(launch_order_block(w->aux, w->soa[w->cur].d, w->d_n, w->block, w->cblock, sp.dt, w->kick_valid ? w->kick : nullptr, w->inv_next));
+    else
+        w->launches += uint64_t(launch_order_morton(w->aux, w->soa[w->cur].d, w->d_n, w->block, w->cblock, sp.dt, w->kick_valid ? w->kick : nullptr, w->inv_next, w->order_temp,
+                                                    w->order_temp_bytes, w->order_keys, w->order_vals, w->order_bounds));
     CU(w, cudaGetLastError());
     CU(w, cudaEventRecord(w->ev_sorted, w->aux));
     w->next_order_pending = true;
@@ -783,6 +809,7 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
     if (const char* e = getenv("OON_MORTON")) w->morton_enabled = atoi(e) != 0;
     if (const char* e = getenv("OON_DEBUG_GPC")) w->debug_gpc = uint32_t(atoi(e));
     if (const char* e = getenv("OON_ASYNC_SORT")) w->async_sort = atoi(e) != 0;
+    if (const char* e = getenv("OON_ORDER_ONE_CTA")) w->order_one_cta = atoi(e) != 0;
     if (const char* e = getenv("OON_MORTON_MIN")) { long v = atol(e); if (v >= 0) w->morton_min_bodies = uint64_t(v); }
     if (const char* e = getenv("OON_RESORT_EVERY")) { long v = atol(e); if (v > 0) w->resort_every = uint32_t(v); }
     auto bail = [&](int code) { std::string msg = w->error; oon_destroy(w); g_create_error = msg; return code; };
@@ -1097,6 +1124,8 @@ int oon_step_profiled(oon_world* w, float dt, uint32_t nsteps, float ms[4], uint
     CHECK_W(w);
     Prof prof; prof.on = true;
     int rc = step_impl(w, dt, nsteps, &prof);
+    const int crc = prof_collect(w, &prof);
+    if (rc == OON_OK) rc = crc;
     if (ms) std::memcpy(ms, prof.ms, sizeof prof.ms);
     if (launches) std::memcpy(launches, prof.launches, sizeof prof.launches);
     return rc;
@@ -1131,9 +1160,25 @@ int oon_sweep_expired(oon_world* w, uint64_t player_ndx) {
     return do_sweep(w, uint32_t(player_ndx), nullptr);
 }
 
+// Peer-to-peer exchange: a kernel that gave up waiting for a peer's slice has produced garbage; make that a sticky error.
+static int check_peers_arrived(oon_world* w) {
+    if (!w->p2p) return OON_OK;
+    uint32_t t = 0;
+    CU(w, cudaMemcpyAsync(&t, w->timeouts, sizeof t, cudaMemcpyDeviceToHost, w->stream));
+    CU(w, cudaStreamSynchronize(w->stream));
+    if (t) return fail(w, OON_ERR_NCCL, "peer-to-peer exchange: %u waits for a peer's slice timed out (a rank fell out of step)", t);
+    return OON_OK;
+}
+
 int oon_synchronize(oon_world* w) {
     CHECK_W(w);
     CU(w, cudaStreamSynchronize(w->stream));
+    return check_peers_arrived(w);
+}
+
+int oon_exchange_kind(const oon_world* w, int* kind) {
+    if (!w || !kind) return OON_ERR_INVALID;
+    *kind = w->nranks == 1 ? OON_EXCHANGE_NONE : (w->p2p ? OON_EXCHANGE_PEER_STORES : OON_EXCHANGE_NCCL_ALLGATHER);
     return OON_OK;
 }
 
@@ -1144,6 +1189,7 @@ int oon_drain_events(oon_world* w, oon_events* out) {
     CU(w, cudaMemcpyAsync(c, w->counters, sizeof c, cudaMemcpyDeviceToHost, w->stream));
     CU(w, cudaMemsetAsync(w->counters, 0, sizeof(unsigned long long) * C_CAPTURE_COLL, w->stream));   // capture cursors live on
     CU(w, cudaStreamSynchronize(w->stream));
+    { int prc = check_peers_arrived(w); if (prc) return prc; }
     out->steps = w->steps; w->steps = 0;
     out->collisions = c[C_COLLISIONS]; out->touches = c[C_TOUCHES]; out->player_touches = c[C_PLAYER_TOUCHES];
     out->terminated = c[C_TERMINATED]; out->removed = c[C_REMOVED];

@@ -128,6 +128,11 @@ int launch_order_morton(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint3
                         const float2* last_kick, uint32_t* inv, void* temp, size_t temp_bytes, unsigned long long* keys2 /* 2*slots */, uint32_t* vals_in /* slots */,
                         uint32_t* stats /* 8 x 16 words */);
 
+// The same order in one launch, one CTA per canonical block, when a block fits one CTA (order_fits_one_cta).
+bool order_fits_one_cta(uint32_t cblock);
+int launch_order_block(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint32_t slots, uint32_t cblock, float predict_dt,
+                       const float2* last_kick, uint32_t* inv);
+
 // update_intrinsic + pack the shard's slice of the exchange buffer (one thread per slot, one block per tile).
 // body_base = global index of local body 0.  Slots >= n are written dead.
 int launch_intrinsic_pack(cudaStream_t st, BodySoA soa, const uint32_t* inv, const uint32_t* d_n, uint32_t slots,

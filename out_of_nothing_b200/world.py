@@ -202,6 +202,12 @@ class World:
         self._check(self._L.oon_timer_stop(self._h, ctypes.byref(ms)))
         return ms.value
 
+    def exchange_kind(self) -> str:
+        """How a sharded world moves its exchange tiles: 'none' (one GPU), 'nccl_allgather' or 'peer_stores' (NVLink peer memory)."""
+        k = ctypes.c_int()
+        self._check(self._L.oon_exchange_kind(self._h, ctypes.byref(k)))
+        return ("none", "nccl_allgather", "peer_stores")[k.value]
+
     def launch_count(self) -> int:
         n = ctypes.c_uint64()
         self._check(self._L.oon_launch_count(self._h, ctypes.byref(n)))

@@ -8,7 +8,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run(rank, nranks, nccl_id, bodies_path, out_path, mode, steps, dt, props):
+def run(rank, nranks, nccl_id, bodies_path, out_path, mode, steps, dt, props, p2p=True, split_steps=False):
+    os.environ["OON_P2P"] = "1" if p2p else "0"
     from out_of_nothing_b200 import capi
     from out_of_nothing_b200.world import World
     bodies = np.load(bodies_path)
@@ -16,11 +17,19 @@ def run(rank, nranks, nccl_id, bodies_path, out_path, mode, steps, dt, props):
     w.set_props(**props)
     w.math_mode = mode
     w.upload(bodies)
-    w.step(dt, steps)
+    if split_steps:                      # the three virtuals one at a time + a re-upload of the same table in between
+        for k in range(steps):
+            w.update_intrinsic(dt); w.update_pairwise(dt); w.update_global(dt)
+            if k == steps // 2:
+                w.upload(w.download())
+    else:
+        w.step(dt, steps)
     out = w.download()
     xyr = w.download_render()
     ev = w.drain_events()
     np.save(out_path % rank, out)
     np.save((out_path % rank) + ".xyr.npy", xyr)
     np.save((out_path % rank) + ".ev.npy", np.array([ev["collisions"], ev["touches"]], np.int64))
+    with open((out_path % rank) + ".kind", "w") as f:
+        f.write(w.exchange_kind())
     w.close()

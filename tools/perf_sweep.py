@@ -22,7 +22,7 @@ ev = w.drain_events()
 prof, _ = w.step_profiled(cfg["dt"], 16)
 print("%%.4f ms/step  interact %%.4f  checked %%.3f" %% (best, prof["interact"] / 16, ev["warp_tiles_checked"] / max(1, ev["warp_tiles"])))
 ''' % ROOT
-libs = sorted(glob.glob(os.path.join(ROOT, "out_of_nothing_b200/lib/variants/*.so")))
+libs = sorted(glob.glob(os.path.join(ROOT, "out_of_nothing_b200/lib/variants/*.so"))) or [os.path.join(ROOT, "out_of_nothing_b200/lib/liboon_gpu.so")]
 for lib in libs:
     env = dict(os.environ, OON_GPU_LIB=lib)
     out = subprocess.run([sys.executable, "-c", CHILD], env=env, capture_output=True, text=True)

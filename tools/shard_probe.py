@@ -27,9 +27,13 @@ for frac in (int(x) for x in os.environ.get('PROBE_FRAC', '2,4,8').split(',')):
             w = World(0); w.set_props(**cfg["props"]); w.upload(state)
             w.step(cfg["dt"], 2); w.synchronize()
             if frac > 1: os.environ["OON_DEBUG_TARGET_FRACTION"] = str(frac)
-            best = 1e9
-            for rep in range(3):
-                prof, _ = w.step_profiled(cfg["dt"], 4)
-                best = min(best, prof["interact"] / 4)
-            print("1/%d shard  group_tiles %d gpc %2d: interact %.4f ms (ideal %.4f)" % (frac, group, cpc, best, 3.02 / frac))
+            parts = []
+            for part in range(frac if os.environ.get("PROBE_PARTS") else 1):
+                os.environ["OON_DEBUG_TARGET_PART"] = str(part)
+                best = 1e9
+                for rep in range(3):
+                    prof, _ = w.step_profiled(cfg["dt"], 2)
+                    best = min(best, prof["interact"] / 2)
+                parts.append(best)
+            print("1/%d shard  group_tiles %d gpc %2d: interact %s ms (ideal %.4f)" % (frac, group, cpc, " ".join("%.4f" % x for x in parts), 3.02 / frac))
             w.close()
