@@ -105,7 +105,7 @@ struct oon_world {
     void* ipc_stage = nullptr;                           // device staging for the handle exchange
     float* peer_tiles[2][8] = {};                        // peers' exchange buffers (imported), indexed by rank
     uint32_t* peer_flags[8] = {};                        // peers' flag arrays (imported)
-    uint32_t group_tiles_override = 0, debug_gpc = 0;
+    uint32_t group_tiles_override = 0, debug_gpc = 0, tail_waves_x2 = 3;
     float4* scratch4 = nullptr;                          // player-only reaction buffer, one float4 per slot
     size_t tiles_cap_slots = 0;                          // slots the exchange buffer (and scratch4) can hold
     float2* kick = nullptr; uint32_t kick_cap = 0; bool kick_valid = false;
@@ -362,20 +362,29 @@ int layout(oon_world* w, uint64_t n_total, uint32_t keep) {
 uint32_t total_tiles(const oon_world* w) { return uint32_t(uint64_t(w->block) * w->nranks / TS); }
 
 // Canonical groups of source tiles: FP32 sums inside a group, exact sums across groups.  The group size is a function
-// of the world size only (it fixes the rounding of the result); how many groups one CTA walks is launch geometry and
-// free to choose: many short CTAs balance best (measured: 4-5 tiles per CTA beats 27 on 1 GPU and 9 on a 1/8 shard),
-// very large worlds walk more groups per CTA so that the grid stays below ~64 waves.
-void grouping(const oon_world* w, uint32_t& group_tiles, uint32_t& gpc) {
+// of the world size only (it fixes the rounding of the result).  How the groups are dealt to CTAs is launch geometry
+// and free to choose: the bulk goes to CTAs that walk `gpc` groups (the first y_big rows of the grid), the last
+// ~1.5 waves' worth to CTAs of one group each, so that the SMs run dry together (a 1/8 shard of the 100k-body world is
+// only ~8 waves of uniform CTAs: 8.1 waves cost 9).
+void grouping(const oon_world* w, uint32_t& group_tiles, uint32_t& gpc, uint32_t& y_big) {
     const uint32_t ntiles = total_tiles(w);
-    group_tiles = ntiles >= 128 ? 4u : ntiles >= 32 ? 2u : 1u;
+    group_tiles = ntiles >= 32 ? 2u : 1u;
     if (w->group_tiles_override) group_tiles = w->group_tiles_override;      // experiments only: changes the rounding
     const uint64_t ngroups = (ntiles + group_tiles - 1) / group_tiles;
     const uint64_t target_blocks = (uint64_t(w->block) + K1_TARGETS_PER_CTA - 1) / K1_TARGETS_PER_CTA;
-    const uint64_t max_ctas = uint64_t(w->sm_count) * 4 * 64;
-    uint64_t g = (target_blocks * ngroups + max_ctas - 1) / max_ctas;
-    g = std::max<uint64_t>(g, (ngroups + 65534) / 65535);                     // gridDim.y limit
-    gpc = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(g, ngroups)));
-    if (w->debug_gpc) gpc = uint32_t(std::min<uint64_t>(w->debug_gpc, ngroups));   // tuning experiments only
+    const uint64_t slots = uint64_t(w->sm_count) * 4;                         // resident CTAs
+    // long CTAs: ~8 tiles, more for very large worlds (keep the grid below ~64 waves and gridDim.y below 65535)
+    uint64_t g = std::max<uint64_t>(1, 8 / group_tiles);
+    g = std::max<uint64_t>(g, (target_blocks * ngroups + slots * 64 - 1) / (slots * 64));
+    g = std::max<uint64_t>(g, (ngroups + 60000) / 60001);
+    if (w->debug_gpc) g = w->debug_gpc;                                        // tuning experiments only
+    g = std::min<uint64_t>(g, ngroups);
+    // short CTAs: the last rows of the grid, about tail_waves waves of them
+    uint64_t ys = g > 1 ? (slots * w->tail_waves_x2 / 2 + target_blocks - 1) / target_blocks : 0;
+    ys = std::min<uint64_t>(ys, std::min<uint64_t>(ngroups, 4000));
+    const uint64_t yb = (ngroups - ys) / g;
+    gpc = uint32_t(g);
+    y_big = uint32_t(yb);
 }
 
 int ensure_partial(oon_world* w) {
@@ -608,11 +617,11 @@ int do_intrinsic_pack(oon_world* w, const StepParams& sp, bool intrinsic, Prof* 
 }
 
 int do_interact(oon_world* w, const StepParams& sp, Prof* prof) {
-    uint32_t group_tiles = 1, gpc = 1;
+    uint32_t group_tiles = 1, gpc = 1, y_big = 0;
     const bool fast_n2n = sp.n2n && !sp.exact;
     int rc;
     if (fast_n2n) {
-        grouping(w, group_tiles, gpc);
+        grouping(w, group_tiles, gpc, y_big);
         if (w->acc_dirty) {                                // only after a (re)allocation or a pass nobody integrated
             CU(w, cudaMemsetAsync(w->acc, 0, sizeof(unsigned long long) * 2 * FX_LIMBS * w->acc_cap, w->stream));
             CU(w, cudaMemsetAsync(w->touch, 0, sizeof(uint32_t) * w->acc_cap, w->stream));
@@ -620,9 +629,17 @@ int do_interact(oon_world* w, const StepParams& sp, Prof* prof) {
         w->acc_dirty = true;
     } else if ((rc = ensure_partial(w))) return rc;
     const ExchangeView xv = xview(w);
+    const float* tiles_in = w->tiles;
+    if (getenv("OON_DEBUG_COPY_TILES") && !w->p2p) {       // experiment: does it matter that the peers wrote the buffer?
+        static float* copy = nullptr; static size_t cap = 0;
+        const size_t bytes = size_t(total_tiles(w)) * TILE_BYTES;
+        if (cap < bytes) { cudaFree(copy); cudaMalloc(&copy, bytes); cap = bytes; }
+        CU(w, cudaMemcpyAsync(copy, w->tiles, bytes, cudaMemcpyDeviceToDevice, w->stream));
+        tiles_in = copy;
+    }
     rc = timed(w, prof, 0, [&](int& launched) -> int {
         if (sp.n2n)
-            launched = launch_interact(w->stream, w->tiles, total_tiles(w), group_tiles, gpc, uint32_t(w->rank) * w->block, w->block,
+            launched = launch_interact(w->stream, tiles_in, total_tiles(w), group_tiles, gpc, y_big, uint32_t(w->rank) * w->block, w->block,
                                        w->d_n, w->soa[w->cur].d, uint32_t(w->rank) * w->block, sp, xv, w->acc, w->touch, w->fx_scale, w->partial,
                                        w->counters, w->cap);
         else
@@ -808,6 +825,7 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
     if (const char* e = getenv("OON_P2P")) w->p2p_wanted = atoi(e) != 0;
     if (const char* e = getenv("OON_MORTON")) w->morton_enabled = atoi(e) != 0;
     if (const char* e = getenv("OON_DEBUG_GPC")) w->debug_gpc = uint32_t(atoi(e));
+    if (const char* e = getenv("OON_DEBUG_TAIL_X2")) w->tail_waves_x2 = uint32_t(atoi(e));
     if (const char* e = getenv("OON_ASYNC_SORT")) w->async_sort = atoi(e) != 0;
     if (const char* e = getenv("OON_ORDER_ONE_CTA")) w->order_one_cta = atoi(e) != 0;
     if (const char* e = getenv("OON_MORTON_MIN")) { long v = atol(e); if (v >= 0) w->morton_min_bodies = uint64_t(v); }

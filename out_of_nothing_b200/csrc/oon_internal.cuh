@@ -140,10 +140,11 @@ int launch_intrinsic_pack(cudaStream_t st, BodySoA soa, const uint32_t* inv, con
 
 // The all-pairs pass.  tiles: whole gathered buffer (ntiles tiles).  Targets = local slots [0, slots) living at
 // global slot target_base.  FAST: sources are cut in canonical groups of `group_tiles` tiles (a function of the
-// world size only); one CTA walks `gpc` consecutive groups (launch geometry, free); group sums go to
+// world size only); a CTA of the first y_big grid rows walks `gpc` consecutive groups, the CTAs after them one group
+// each (launch geometry, free: y_big * gpc <= number of groups); group sums go to
 // acc [2 components][FX_LIMBS][slots] (64-bit integer atomics) and touch visits to touch[slots].
 // EXACT: partial[slots] = {new v.x, new v.y, touch visits, -}.
-int launch_interact(cudaStream_t st, const float* tiles, uint32_t ntiles, uint32_t group_tiles, uint32_t gpc,
+int launch_interact(cudaStream_t st, const float* tiles, uint32_t ntiles, uint32_t group_tiles, uint32_t gpc, uint32_t y_big,
                     uint32_t target_base, uint32_t slots, const uint32_t* d_n_local, BodySoA soa, uint32_t body_base,
                     StepParams sp, const ExchangeView& xv, unsigned long long* acc, uint32_t* touch, int* fx_scale, float4* partial,
                     unsigned long long* counters, CaptureBuf cap);

@@ -10,7 +10,7 @@ rank, ws, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.en
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 bodies, cfg = synth.make(os.environ.get("PROBE_WORKLOAD", "c4_cloud_100k"))
-for p2p in (1, 0):
+for p2p in (int(x) for x in os.environ.get('PROBE_P2P', '1,0').split(',')):
     os.environ["OON_P2P"] = str(p2p)
     idt = torch.zeros(capi.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
     if rank == 0:

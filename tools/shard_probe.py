@@ -30,10 +30,11 @@ for frac in (int(x) for x in os.environ.get('PROBE_FRAC', '2,4,8').split(',')):
             parts = []
             for part in range(frac if os.environ.get("PROBE_PARTS") else 1):
                 os.environ["OON_DEBUG_TARGET_PART"] = str(part)
+                nf = int(os.environ.get("PROBE_FRAMES", "2"))
                 best = 1e9
-                for rep in range(3):
-                    prof, _ = w.step_profiled(cfg["dt"], 2)
-                    best = min(best, prof["interact"] / 2)
+                for rep in range(3 if nf < 10 else 1):
+                    prof, _ = w.step_profiled(cfg["dt"], nf)
+                    best = min(best, prof["interact"] / nf)
                 parts.append(best)
             print("1/%d shard  group_tiles %d gpc %2d: interact %s ms (ideal %.4f)" % (frac, group, cpc, " ".join("%.4f" % x for x in parts), 3.02 / frac))
             w.close()
