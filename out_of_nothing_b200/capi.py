@@ -64,7 +64,7 @@ EXPORTS = [
     "oon_synchronize", "oon_drain_events",
     "oon_timer_start", "oon_timer_stop", "oon_step_profiled", "oon_bench_frames", "oon_launch_count", "oon_exchange_kind",
     "oon_measure_fp32_peak", "oon_measure_copy_bandwidth",
-    "oon_debug_capture_pairs", "oon_debug_fetch_pairs", "oon_debug_fetch_kick", "oon_debug_fetch_removed",
+    "oon_debug_capture_pairs", "oon_debug_fetch_pairs", "oon_debug_fetch_kick", "oon_debug_fetch_removed", "oon_debug_time_interact",
 ]
 
 _lib = None
@@ -127,6 +127,7 @@ def load():
     L.oon_debug_fetch_pairs.argtypes = [vp, i32, vp, u64, P(u64)]
     L.oon_debug_fetch_kick.argtypes = [vp, vp, u64, P(u64)]
     L.oon_debug_fetch_removed.argtypes = [vp, vp, u64, P(u64)]
+    L.oon_debug_time_interact.argtypes = [vp, f32, u32, u32, P(f32)]
     for name in EXPORTS:
         if name != "oon_last_error":
             getattr(L, name).restype = i32

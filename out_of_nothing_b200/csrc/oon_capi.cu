@@ -105,7 +105,8 @@ struct oon_world {
     void* ipc_stage = nullptr;                           // device staging for the handle exchange
     float* peer_tiles[2][8] = {};                        // peers' exchange buffers (imported), indexed by rank
     uint32_t* peer_flags[8] = {};                        // peers' flag arrays (imported)
-    uint32_t group_tiles_override = 0, debug_gpc = 0, tail_waves_x2 = 3;
+    uint32_t group_tiles_override = 0, debug_gpc = 0, tail_waves_x2 = 6;
+    uint32_t dbg_fraction = 0, dbg_part = 0;             // oon_debug_time_interact: launch a part of the target blocks
     float4* scratch4 = nullptr;                          // player-only reaction buffer, one float4 per slot
     size_t tiles_cap_slots = 0;                          // slots the exchange buffer (and scratch4) can hold
     float2* kick = nullptr; uint32_t kick_cap = 0; bool kick_valid = false;
@@ -364,17 +365,18 @@ uint32_t total_tiles(const oon_world* w) { return uint32_t(uint64_t(w->block) * 
 // Canonical groups of source tiles: FP32 sums inside a group, exact sums across groups.  The group size is a function
 // of the world size only (it fixes the rounding of the result).  How the groups are dealt to CTAs is launch geometry
 // and free to choose: the bulk goes to CTAs that walk `gpc` groups (the first y_big rows of the grid), the last
-// ~1.5 waves' worth to CTAs of one group each, so that the SMs run dry together (a 1/8 shard of the 100k-body world is
+// ~3 waves' worth to CTAs of one group each, so that the SMs run dry together (a 1/8 shard of the 100k-body world is
 // only ~8 waves of uniform CTAs: 8.1 waves cost 9).
 void grouping(const oon_world* w, uint32_t& group_tiles, uint32_t& gpc, uint32_t& y_big) {
     const uint32_t ntiles = total_tiles(w);
-    group_tiles = ntiles >= 32 ? 2u : 1u;
+    group_tiles = ntiles >= 128 ? 4u : ntiles >= 32 ? 2u : 1u;
     if (w->group_tiles_override) group_tiles = w->group_tiles_override;      // experiments only: changes the rounding
     const uint64_t ngroups = (ntiles + group_tiles - 1) / group_tiles;
-    const uint64_t target_blocks = (uint64_t(w->block) + K1_TARGETS_PER_CTA - 1) / K1_TARGETS_PER_CTA;
+    uint64_t target_blocks = (uint64_t(w->block) + K1_TARGETS_PER_CTA - 1) / K1_TARGETS_PER_CTA;
+    if (w->dbg_fraction > 1) target_blocks = (target_blocks + w->dbg_fraction - 1) / w->dbg_fraction;
     const uint64_t slots = uint64_t(w->sm_count) * 4;                         // resident CTAs
-    // long CTAs: ~8 tiles, more for very large worlds (keep the grid below ~64 waves and gridDim.y below 65535)
-    uint64_t g = std::max<uint64_t>(1, 8 / group_tiles);
+    // long CTAs: ~16 tiles, more for very large worlds (keep the grid below ~64 waves and gridDim.y below 65535)
+    uint64_t g = std::max<uint64_t>(1, 16 / group_tiles);
     g = std::max<uint64_t>(g, (target_blocks * ngroups + slots * 64 - 1) / (slots * 64));
     g = std::max<uint64_t>(g, (ngroups + 60000) / 60001);
     if (w->debug_gpc) g = w->debug_gpc;                                        // tuning experiments only
@@ -641,7 +643,7 @@ int do_interact(oon_world* w, const StepParams& sp, Prof* prof) {
         if (sp.n2n)
             launched = launch_interact(w->stream, tiles_in, total_tiles(w), group_tiles, gpc, y_big, uint32_t(w->rank) * w->block, w->block,
                                        w->d_n, w->soa[w->cur].d, uint32_t(w->rank) * w->block, sp, xv, w->acc, w->touch, w->fx_scale, w->partial,
-                                       w->counters, w->cap);
+                                       w->counters, w->cap, w->dbg_fraction, w->dbg_part);
         else
             launched = launch_wait_peers(w->stream, xv) +
                        launch_interact_player_only(w->stream, w->tiles, total_tiles(w), uint32_t(w->rank) * w->block, w->block, w->d_n,
@@ -776,6 +778,26 @@ bool mortal(float lifetime) { return lifetime > 0.f || (lifetime != LIFETIME_UNL
 extern "C" {
 
 int oon_abi_version(void) { return OON_ABI_VERSION; }
+
+int oon_debug_time_interact(oon_world* w, float dt, uint32_t fraction, uint32_t part, float* ms) {
+    CHECK_W(w);
+    if (!ms) return fail(w, OON_ERR_INVALID, "null output");
+    if (!w->tiles_fresh || !w->block) return fail(w, OON_ERR_INVALID, "oon_debug_time_interact: call oon_update_intrinsic first");
+    const StepParams sp = step_params(w, dt);
+    if (!sp.n2n || sp.exact) return fail(w, OON_ERR_UNSUPPORTED, "oon_debug_time_interact times the FAST all-pairs kernel only");
+    w->dbg_fraction = fraction; w->dbg_part = part;
+    CU(w, cudaEventRecord(w->ev_start, w->stream));
+    int rc = do_interact(w, sp, nullptr);
+    w->dbg_fraction = 0; w->dbg_part = 0;
+    if (rc) return rc;
+    CU(w, cudaEventRecord(w->ev_stop, w->stream));
+    CU(w, cudaMemsetAsync(w->acc, 0, sizeof(unsigned long long) * 2 * FX_LIMBS * w->acc_cap, w->stream));   // the pass never happened
+    CU(w, cudaMemsetAsync(w->touch, 0, sizeof(uint32_t) * w->acc_cap, w->stream));
+    w->acc_dirty = false;
+    CU(w, cudaEventSynchronize(w->ev_stop));
+    CU(w, cudaEventElapsedTime(ms, w->ev_start, w->ev_stop));
+    return OON_OK;
+}
 
 const char* oon_last_error(const oon_world* w) { return w ? w->error.c_str() : g_create_error.c_str(); }
 

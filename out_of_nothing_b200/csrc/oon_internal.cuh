@@ -147,7 +147,7 @@ int launch_intrinsic_pack(cudaStream_t st, BodySoA soa, const uint32_t* inv, con
 int launch_interact(cudaStream_t st, const float* tiles, uint32_t ntiles, uint32_t group_tiles, uint32_t gpc, uint32_t y_big,
                     uint32_t target_base, uint32_t slots, const uint32_t* d_n_local, BodySoA soa, uint32_t body_base,
                     StepParams sp, const ExchangeView& xv, unsigned long long* acc, uint32_t* touch, int* fx_scale, float4* partial,
-                    unsigned long long* counters, CaptureBuf cap);
+                    unsigned long long* counters, CaptureBuf cap, uint32_t dbg_fraction = 0, uint32_t dbg_part = 0);
 // Peer-to-peer exchange: hold the stream until every peer's slice of epoch xv.epoch has landed (for the kernels that
 // read the exchange buffer without waiting themselves).
 int launch_wait_peers(cudaStream_t st, const ExchangeView& xv);

@@ -208,6 +208,12 @@ class World:
         self._check(self._L.oon_exchange_kind(self._h, ctypes.byref(k)))
         return ("none", "nccl_allgather", "peer_stores")[k.value]
 
+    def debug_time_interact(self, dt: float, fraction: int, part: int = 0) -> float:
+        """ms of one FAST all-pairs launch over one of `fraction` parts of the targets; the world is left unchanged."""
+        ms = ctypes.c_float()
+        self._check(self._L.oon_debug_time_interact(self._h, dt, fraction, part, ctypes.byref(ms)))
+        return ms.value
+
     def launch_count(self) -> int:
         n = ctypes.c_uint64()
         self._check(self._L.oon_launch_count(self._h, ctypes.byref(n)))
