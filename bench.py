@@ -221,8 +221,12 @@ def main():
     value = args.steps * inter_per_step / (ms * 1e-3)
 
     # ---- per-kernel device time (events on the launching stream) for the roofline lines
-    prof_steps = 5
-    prof_ms, prof_launches = w.step_profiled(dt, prof_steps)
+    # (same regime as the timed region: L2 flushed before every frame, one event pair per kernel class, no host round trips)
+    prof_steps = 20
+    if flush_bytes:
+        _, prof_ms, prof_launches = w.bench_frames_profiled(dt, prof_steps, flush_bytes)
+    else:
+        prof_ms, prof_launches = w.step_profiled(dt, prof_steps)
     lo, hi = sharding.shard_range(n_start, rank, world_size)
     local_inter = (hi - lo) * (n_start - 1)
     k1_ms = prof_ms["interact"] / max(1, prof_launches["interact"])

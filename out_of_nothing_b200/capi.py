@@ -62,7 +62,7 @@ EXPORTS = [
     "oon_add_bodies", "oon_remove_body", "oon_get_body", "oon_set_body",
     "oon_step", "oon_update_intrinsic", "oon_update_pairwise", "oon_update_global", "oon_sweep_expired",
     "oon_synchronize", "oon_drain_events",
-    "oon_timer_start", "oon_timer_stop", "oon_step_profiled", "oon_bench_frames", "oon_launch_count", "oon_exchange_kind",
+    "oon_timer_start", "oon_timer_stop", "oon_step_profiled", "oon_bench_frames", "oon_bench_frames_profiled", "oon_launch_count", "oon_exchange_kind",
     "oon_measure_fp32_peak", "oon_measure_copy_bandwidth",
     "oon_debug_capture_pairs", "oon_debug_fetch_pairs", "oon_debug_fetch_kick", "oon_debug_fetch_removed", "oon_debug_time_interact",
 ]
@@ -119,6 +119,7 @@ def load():
     L.oon_timer_stop.argtypes = [vp, P(f32)]
     L.oon_step_profiled.argtypes = [vp, f32, u32, P(f32), P(u32)]
     L.oon_bench_frames.argtypes = [vp, f32, u32, u64, P(ctypes.c_double)]
+    L.oon_bench_frames_profiled.argtypes = [vp, f32, u32, u64, P(ctypes.c_double), P(f32), P(u32)]
     L.oon_launch_count.argtypes = [vp, P(u64)]
     L.oon_exchange_kind.argtypes = [vp, P(ctypes.c_int)]
     L.oon_measure_fp32_peak.argtypes = [i32, P(ctypes.c_double)]

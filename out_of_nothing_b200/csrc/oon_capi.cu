@@ -1251,7 +1251,7 @@ int oon_timer_stop(oon_world* w, float* elapsed_ms) {
     return OON_OK;
 }
 
-int oon_bench_frames(oon_world* w, float dt, uint32_t nsteps, uint64_t flush_bytes, double* ms_sum) {
+static int bench_frames_impl(oon_world* w, float dt, uint32_t nsteps, uint64_t flush_bytes, double* ms_sum, Prof* prof) {
     CHECK_W(w);
     if (!ms_sum) return fail(w, OON_ERR_INVALID, "null output");
     *ms_sum = 0.0;
@@ -1263,11 +1263,19 @@ int oon_bench_frames(oon_world* w, float dt, uint32_t nsteps, uint64_t flush_byt
     for (auto& e : ev) if (cudaEventCreate(&e) != cudaSuccess) { rc = fail(w, OON_ERR_CUDA, "cudaEventCreate failed"); break; }
     for (uint32_t k = 0; k < nsteps && rc == OON_OK; ++k) {
         if (flush && cudaMemsetAsync(flush, int(k & 0xff), flush_bytes, w->stream) != cudaSuccess) { rc = fail(w, OON_ERR_CUDA, "flush memset failed"); break; }
+        if (flush && w->nranks > 1) {
+            // The ranks of a sharded world wait for each other inside the frame: line them up again after the untimed flush
+            // (a one-word all-gather on the stream), or the slowest rank's flush would be charged to everybody's frame.
+            if (g_nccl.AllGather(static_cast<char*>(w->ipc_stage) + size_t(w->rank) * 4, w->ipc_stage, 4, ncclChar, w->comm, w->stream) != ncclSuccess) {
+                rc = fail(w, OON_ERR_NCCL, "alignment all-gather failed"); break;
+            }
+        }
         if (cudaEventRecord(ev[2 * k], w->stream) != cudaSuccess) { rc = fail(w, OON_ERR_CUDA, "cudaEventRecord failed"); break; }
-        rc = step_impl(w, dt, 1, nullptr);
+        rc = step_impl(w, dt, 1, prof);
         if (rc == OON_OK && cudaEventRecord(ev[2 * k + 1], w->stream) != cudaSuccess) rc = fail(w, OON_ERR_CUDA, "cudaEventRecord failed");
     }
     if (rc == OON_OK && cudaStreamSynchronize(w->stream) != cudaSuccess) rc = fail(w, OON_ERR_CUDA, "synchronize failed");
+    if (prof) { const int crc = prof_collect(w, prof); if (rc == OON_OK) rc = crc; }
     if (rc == OON_OK) {
         for (uint32_t k = 0; k < nsteps; ++k) {
             float ms = 0.f;
@@ -1277,6 +1285,18 @@ int oon_bench_frames(oon_world* w, float dt, uint32_t nsteps, uint64_t flush_byt
     }
     for (auto& e : ev) if (e) cudaEventDestroy(e);
     if (flush) cudaFree(flush);
+    return rc;
+}
+
+int oon_bench_frames(oon_world* w, float dt, uint32_t nsteps, uint64_t flush_bytes, double* ms_sum) {
+    return bench_frames_impl(w, dt, nsteps, flush_bytes, ms_sum, nullptr);
+}
+
+int oon_bench_frames_profiled(oon_world* w, float dt, uint32_t nsteps, uint64_t flush_bytes, double* ms_sum, float ms[4], uint32_t launches[4]) {
+    Prof prof; prof.on = true;
+    const int rc = bench_frames_impl(w, dt, nsteps, flush_bytes, ms_sum, &prof);
+    if (ms) std::memcpy(ms, prof.ms, sizeof prof.ms);
+    if (launches) std::memcpy(launches, prof.launches, sizeof prof.launches);
     return rc;
 }
 

@@ -187,6 +187,15 @@ class World:
         self._check(self._L.oon_bench_frames(self._h, dt, nsteps, flush_bytes, ctypes.byref(ms)))
         return ms.value
 
+    def bench_frames_profiled(self, dt: float, nsteps: int, flush_bytes: int = 0):
+        """bench_frames with per-kernel-class event pairs as well -> (total ms, {class: ms}, {class: launches})."""
+        total = ctypes.c_double()
+        ms = (ctypes.c_float * 4)()
+        launches = (ctypes.c_uint32 * 4)()
+        self._check(self._L.oon_bench_frames_profiled(self._h, dt, nsteps, flush_bytes, ctypes.byref(total), ms, launches))
+        names = ("interact", "integrate", "exchange", "sweep")
+        return total.value, {k: float(ms[i]) for i, k in enumerate(names)}, {k: int(launches[i]) for i, k in enumerate(names)}
+
     def synchronize(self): self._check(self._L.oon_synchronize(self._h))
 
     def drain_events(self) -> dict:

@@ -22,9 +22,11 @@ for p2p in (int(x) for x in os.environ.get('PROBE_P2P', '1,0').split(',')):
     dist.barrier()
     w.timer_start(); w.step(cfg["dt"], 50); total = w.timer_stop() / 50
     prof, launches = w.step_profiled(cfg["dt"], 50)
+    ftotal, fprof, _ = w.bench_frames_profiled(cfg["dt"], 50, 256 << 20)
     ev = w.drain_events()
     row = {"rank": rank, "kind": w.exchange_kind(), "ms_per_step": round(total, 4), **{k: round(v / 50, 4) for k, v in prof.items()},
-           "checked": round(ev["warp_tiles_checked"] / max(1, ev["warp_tiles"]), 3)}
+           "checked": round(ev["warp_tiles_checked"] / max(1, ev["warp_tiles"]), 3),
+           "flushed": {"ms_per_step": round(ftotal / 50, 4), **{k: round(v / 50, 4) for k, v in fprof.items()}}}
     rows = [None] * ws
     dist.all_gather_object(rows, row)
     if rank == 0:
