@@ -19,6 +19,9 @@
 //   /root/reference/src/app/model/World.cpp:532-548  touch_hook
 //   /root/reference/src/app/model/Entity.hpp:25-98, Entity.cpp:14-26
 //   /root/reference/src/app/OON.cpp:1083-1095        the caller's expired-body sweep
+//   /root/reference/src/app/model/Emitter.hpp:24-37, Emitter.cpp:22-92   Emitter::Config, emit_particles
+//   (the reference draws from the C library's unseeded rand(); here every draw is oon_rand(seed, k), a
+//   counter-based stand-in with the MSVC RAND_MAX the reference ships with — see EmitterConfig below)
 //
 // Why a restatement: the reference cannot be compiled here.  Every translation unit
 // includes headers of the author's separate engine (O2N 0.98: Szim/..., sz/..., Tracy),
@@ -135,6 +138,36 @@ struct Properties {  // World.hpp:59-69, defaults World.cpp:42-50
     bool interact_n2n = false;
     double repulsion_stiffness = 0;
     CollisionMode collision_mode = CollisionMode::Glide_Through;
+};
+
+// --- Emitter (Emitter.hpp:24-37) ----------------------------------------------------------------
+// rand() replacement ("a seeded RNG replacing rand()"): draw k of a burst is
+// oon_rand(seed, k) in [0, RAND_MAX], RAND_MAX = 32767 as in the MSVC runtime the reference ships with.
+// Particle i of a burst uses draws 5i+0 (mass), 5i+1, 5i+2 (p.x, p.y), 5i+3, 5i+4 (v.x, v.y) — the order in
+// which Emitter.cpp:49-71 evaluates its rand() calls — whether or not the particle is emitted.
+inline constexpr int OON_RAND_MAX = 32767;
+inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+inline int oon_rand(uint64_t seed, uint64_t k) { return int(splitmix64(seed ^ (k * 0xD1342543DE82EF95ull)) >> 49); }
+
+template <class Num>
+struct EmitterConfig {
+    V2<Num> eject_velocity{};
+    V2<Num> eject_offset{};
+    Num v_factor = Num(0.1f);
+    Num offset_velo_factor = Num(0.2f);
+    float particle_lifetime = -1;
+    bool create_mass = true;
+    Num particle_density = Phys<Num>::DENSITY_ROCK * Num(0.001f);
+    V2<Num> position_divergence{Num(5), Num(5)};
+    Num velocity_divergence = Num(1);
+    Num particle_mass_min{};
+    Num particle_mass_max{};
+    uint32_t color = 0x706080;
 };
 
 struct PairEvent { uint32_t target, source; };
@@ -285,6 +318,47 @@ public:
                 remove_body(i);
             }
         }
+    }
+
+    // Emitter::emit_particles, Emitter.cpp:22-92.  nozzles: n positions relative to the emitter, or nullptr.
+    // Returns the number of particles appended.
+    unsigned emit_particles(size_t emitter_id, unsigned n, const EmitterConfig<Num>& cfg, const V2<Num>* nozzles, uint64_t seed) {
+        const Num RM = Num(OON_RAND_MAX);
+        unsigned emitted = 0;
+        // (the reference holds a reference to the emitter; bodies are shared_ptrs, so push_back does not move it)
+        EntityT& emitter = *bodies[emitter_id];
+        V2<Num> p_range{cfg.position_divergence.x * emitter.r, cfg.position_divergence.y * emitter.r};
+        V2<Num> p_offset = cfg.eject_offset;
+        {
+            // emitter.v.normalized() * cfg.offset_velo_factor * emitter.r; the null vector normalises to itself
+            // ("always checked implicitly", Emitter.cpp:41-43)
+            const Num l = emitter.v.length();
+            V2<Num> nv = l == 0 ? V2<Num>{} : V2<Num>{emitter.v.x / l, emitter.v.y / l};
+            V2<Num> add = nv * cfg.offset_velo_factor * emitter.r;
+            p_offset += add;
+        }
+        const Num v_range = emitter.r * cfg.velocity_divergence;
+        for (unsigned i = 0; i < n; ++i) {
+            const uint64_t k = uint64_t(i) * 5;
+            const Num particle_mass = cfg.particle_mass_min + (cfg.particle_mass_max - cfg.particle_mass_min) * float(oon_rand(seed, k)) / RM;
+            if (!cfg.create_mass && emitter.mass < particle_mass) continue;
+            V2<Num> p{(Num(oon_rand(seed, k + 1)) * p_range.x) / RM - p_range.x / 2 + emitter.p.x + p_offset.x,
+                      (Num(oon_rand(seed, k + 2)) * p_range.y) / RM - p_range.y / 2 + emitter.p.y + p_offset.y};
+            if (nozzles) p += nozzles[i] * emitter.r;
+            EntityT e;
+            e.lifetime = cfg.particle_lifetime;
+            e.density = cfg.particle_density;
+            e.p = p;
+            e.v = {(Num(oon_rand(seed, k + 3)) * v_range) / RM - v_range / 2 + emitter.v.x * cfg.v_factor + cfg.eject_velocity.x,
+                   (Num(oon_rand(seed, k + 4)) * v_range) / RM - v_range / 2 + emitter.v.y * cfg.v_factor + cfg.eject_velocity.y};
+            e.color = cfg.color;
+            e.mass = particle_mass;
+            add_body(e);
+            ++emitted;
+            if (!cfg.create_mass) emitter.mass -= particle_mass;
+        }
+        if (!cfg.create_mass) emitter.recalc();
+        return emitted;
     }
 
     // One frame of OONApp::updates_for_next_frame's model part (OON.cpp:1085-1095).

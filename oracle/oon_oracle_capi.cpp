@@ -5,6 +5,7 @@
 
 #include <chrono>
 #include <cstring>
+#include <type_traits>
 #include <variant>
 
 using namespace oon_oracle;
@@ -180,6 +181,29 @@ double oracle_time_steps(void* p, float dt, uint32_t nsteps, int sweep) {
     auto t1 = std::chrono::steady_clock::now();
     return std::chrono::duration<double>(t1 - t0).count();
 }
+
+// Emitter::emit_particles (Emitter.cpp:22-92).  cfg = 15 floats in the order of oon_emitter_cfg (include/oon_gpu.h):
+// eject_velocity.xy, eject_offset.xy, v_factor, offset_velo_factor, particle_lifetime, create_mass, particle_density,
+// position_divergence.xy, velocity_divergence, particle_mass_min, particle_mass_max, color (as uint32 bits).
+uint32_t oracle_emit_particles(void* p, uint64_t emitter_id, uint32_t n, const float* c, const float* nozzles, uint64_t seed) {
+    auto* h = static_cast<Handle*>(p);
+    auto run = [&](auto& w) -> uint32_t {
+        using Num = std::decay_t<decltype(w.bodies[0]->r)>;
+        if (emitter_id >= w.bodies.size()) return 0;
+        EmitterConfig<Num> cfg;
+        cfg.eject_velocity = {Num(c[0]), Num(c[1])}; cfg.eject_offset = {Num(c[2]), Num(c[3])};
+        cfg.v_factor = Num(c[4]); cfg.offset_velo_factor = Num(c[5]); cfg.particle_lifetime = c[6]; cfg.create_mass = c[7] != 0.f;
+        cfg.particle_density = Num(c[8]); cfg.position_divergence = {Num(c[9]), Num(c[10])}; cfg.velocity_divergence = Num(c[11]);
+        cfg.particle_mass_min = Num(c[12]); cfg.particle_mass_max = Num(c[13]);
+        uint32_t color; std::memcpy(&color, &c[14], 4); cfg.color = color;
+        std::vector<V2<Num>> nz;
+        if (nozzles) for (uint32_t i = 0; i < n; ++i) nz.push_back({Num(nozzles[2 * i]), Num(nozzles[2 * i + 1])});
+        return w.emit_particles(size_t(emitter_id), n, cfg, nozzles ? nz.data() : nullptr, seed);
+    };
+    return h->is_double ? run(h->wd) : run(h->wf);
+}
+
+int oracle_rand(uint64_t seed, uint64_t k) { return oon_rand(seed, k); }
 
 float oracle_radius_from_mass_and_density_f32(float mass, float density) {
     return Phys<float>::radius_from_mass_and_density(mass, density);

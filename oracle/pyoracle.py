@@ -63,6 +63,10 @@ def lib():
         L.oracle_time_steps.argtypes = [vp, f32, u32, i32]
         L.oracle_radius_from_mass_and_density_f32.restype = f32
         L.oracle_radius_from_mass_and_density_f32.argtypes = [f32, f32]
+        L.oracle_emit_particles.argtypes = [vp, u64, u32, vp, vp, u64]
+        L.oracle_emit_particles.restype = u32
+        L.oracle_rand.argtypes = [u64, u64]
+        L.oracle_rand.restype = i32
         _lib = L
     return _lib
 
@@ -137,6 +141,20 @@ class OracleWorld:
     def update_pairwise(self, dt): self.phase(self.PAIRWISE, dt)
     def update_global(self, dt): self.phase(self.GLOBAL, dt)
     def sweep_expired(self): self.phase(self.SWEEP, 0.0)
+
+    #: field order of the 15-float configuration oracle_emit_particles takes (== Emitter::Config, Emitter.hpp:24-37)
+    EMITTER_FIELDS = ("eject_velocity_x", "eject_velocity_y", "eject_offset_x", "eject_offset_y", "v_factor", "offset_velo_factor",
+                      "particle_lifetime", "create_mass", "particle_density", "position_divergence_x", "position_divergence_y",
+                      "velocity_divergence", "particle_mass_min", "particle_mass_max", "color")
+
+    def emit_particles(self, emitter_id: int, n: int, cfg, nozzles=None, seed: int = 0) -> int:
+        """Emitter::emit_particles (Emitter.cpp:22-92); cfg = any object with the EMITTER_FIELDS attributes."""
+        c = np.zeros(15, np.float32)
+        for i, name in enumerate(self.EMITTER_FIELDS[:14]):
+            c[i] = float(getattr(cfg, name))
+        c[14:15].view(np.uint32)[0] = int(getattr(cfg, "color"))
+        nz = None if nozzles is None else np.ascontiguousarray(nozzles, np.float32)
+        return int(lib().oracle_emit_particles(self._h, emitter_id, n, c.ctypes.data, nz.ctypes.data if nz is not None else None, seed))
 
     def step(self, dt: float, nsteps: int = 1, sweep: bool = True):
         lib().oracle_step(self._h, dt, nsteps, int(sweep))

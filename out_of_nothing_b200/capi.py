@@ -49,6 +49,25 @@ class Props(ctypes.Structure):
     ]
 
 
+class EmitterCfg(ctypes.Structure):
+    """``oon_emitter_cfg`` == Emitter::Config (Emitter.hpp:24-37), float build."""
+
+    _fields_ = [
+        ("eject_velocity_x", ctypes.c_float), ("eject_velocity_y", ctypes.c_float),
+        ("eject_offset_x", ctypes.c_float), ("eject_offset_y", ctypes.c_float),
+        ("v_factor", ctypes.c_float), ("offset_velo_factor", ctypes.c_float),
+        ("particle_lifetime", ctypes.c_float), ("create_mass", ctypes.c_uint32),
+        ("particle_density", ctypes.c_float),
+        ("position_divergence_x", ctypes.c_float), ("position_divergence_y", ctypes.c_float),
+        ("velocity_divergence", ctypes.c_float),
+        ("particle_mass_min", ctypes.c_float), ("particle_mass_max", ctypes.c_float),
+        ("color", ctypes.c_uint32),
+    ]
+
+
+assert ctypes.sizeof(EmitterCfg) == 60
+
+
 class Events(ctypes.Structure):
     _fields_ = [(n, ctypes.c_uint64) for n in ("steps", "collisions", "touches", "player_touches", "terminated", "removed",
                                                 "warp_tiles", "warp_tiles_checked")]
@@ -59,7 +78,7 @@ EXPORTS = [
     "oon_abi_version", "oon_create", "oon_nccl_unique_id", "oon_create_sharded", "oon_destroy", "oon_last_error",
     "oon_props_default", "oon_set_props", "oon_get_props", "oon_set_math_mode", "oon_get_math_mode",
     "oon_upload", "oon_upload_f64", "oon_download", "oon_download_f64", "oon_download_render", "oon_body_count",
-    "oon_add_bodies", "oon_remove_body", "oon_get_body", "oon_set_body",
+    "oon_add_bodies", "oon_remove_body", "oon_get_body", "oon_set_body", "oon_emitter_cfg_default", "oon_emit_particles",
     "oon_step", "oon_update_intrinsic", "oon_update_pairwise", "oon_update_global", "oon_sweep_expired",
     "oon_synchronize", "oon_drain_events",
     "oon_timer_start", "oon_timer_stop", "oon_step_profiled", "oon_bench_frames", "oon_bench_frames_profiled", "oon_launch_count", "oon_exchange_kind",
@@ -108,6 +127,8 @@ def load():
     L.oon_remove_body.argtypes = [vp, u64]
     L.oon_get_body.argtypes = [vp, u64, vp]
     L.oon_set_body.argtypes = [vp, u64, vp]
+    L.oon_emitter_cfg_default.argtypes = [P(EmitterCfg)]
+    L.oon_emit_particles.argtypes = [vp, u64, u32, P(EmitterCfg), vp, u64, P(u32)]
     L.oon_step.argtypes = [vp, f32, u32]
     L.oon_update_intrinsic.argtypes = [vp, f32]
     L.oon_update_pairwise.argtypes = [vp, f32]

@@ -1096,6 +1096,52 @@ int oon_add_bodies(oon_world* w, const oon_body_f32* bodies, uint64_t k) {
     return OON_OK;
 }
 
+int oon_emitter_cfg_default(oon_emitter_cfg* out) {
+    if (!out) return OON_ERR_INVALID;
+    std::memset(out, 0, sizeof *out);
+    out->v_factor = 0.1f;                            // Emitter.hpp:26-36
+    out->offset_velo_factor = 0.2f;
+    out->particle_lifetime = LIFETIME_UNLIMITED;
+    out->create_mass = 1;
+    out->particle_density = 2000.0f * 0.001f;        // Phys::DENSITY_ROCK * 0.001f
+    out->position_divergence_x = out->position_divergence_y = 5.f;
+    out->velocity_divergence = 1.f;
+    out->color = 0x706080u;
+    return OON_OK;
+}
+
+int oon_emit_particles(oon_world* w, uint64_t emitter_ndx, uint32_t n, const oon_emitter_cfg* cfg, const float* nozzles_xy,
+                       uint64_t seed, uint32_t* emitted_out) {
+    CHECK_W(w);
+    { int qrc = quiesce_aux(w); if (qrc) return qrc; }
+    if (emitted_out) *emitted_out = 0;
+    if (!cfg) return fail(w, OON_ERR_INVALID, "null emitter configuration");
+    if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "emit_particles on a sharded world is not implemented in this build");
+    int rc = sync_count(w);
+    if (rc) return rc;
+    if (emitter_ndx >= w->n_local) return fail(w, OON_ERR_INVALID, "emitter index %llu out of range (%u bodies)", (unsigned long long)emitter_ndx, w->n_local);
+    if (!n) return OON_OK;
+    const uint32_t old_n = w->n_local;
+    if ((rc = layout(w, uint64_t(old_n) + n, old_n))) return rc;        // room for all n; the count is corrected below
+    float2* nozzles_dev = nullptr;
+    if (nozzles_xy) {
+        if ((rc = ensure_aos(w, (size_t(n) * sizeof(float2) + sizeof(oon_body_f32) - 1) / sizeof(oon_body_f32)))) return rc;
+        nozzles_dev = reinterpret_cast<float2*>(w->aos_dev);
+        CU(w, cudaMemcpyAsync(nozzles_dev, nozzles_xy, size_t(n) * sizeof(float2), cudaMemcpyHostToDevice, w->stream));
+    }
+    CU(w, cudaMemcpyAsync(w->d_n, &old_n, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+    w->launches += uint64_t(launch_emit(w->stream, w->soa[w->cur].d, w->d_n, uint32_t(emitter_ndx), n, *cfg, nozzles_dev, seed, w->d_removed_count));
+    CU(w, cudaGetLastError());
+    uint32_t emitted = 0;
+    CU(w, cudaMemcpyAsync(&emitted, w->d_removed_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));
+    CU(w, cudaStreamSynchronize(w->stream));
+    if ((rc = layout(w, uint64_t(old_n) + emitted, old_n + emitted))) return rc;   // bookkeeping only: capacity is there
+    if (emitted) w->has_mortals |= mortal(cfg->particle_lifetime);
+    if (emitted_out) *emitted_out = emitted;
+    return OON_OK;
+}
+
 int oon_get_body(oon_world* w, uint64_t ndx, oon_body_f32* out) {
     CHECK_W(w);
     if (!out) return fail(w, OON_ERR_INVALID, "null output");

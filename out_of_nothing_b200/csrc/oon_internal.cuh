@@ -121,6 +121,10 @@ constexpr int FX_MAX_SHIFT = 96;     // 24-bit mantissa << 96 = 120 bits
 int launch_unpack_f32(cudaStream_t st, const oon_body_f32* aos, BodySoA soa, uint32_t first, uint32_t count);
 int launch_pack_f32(cudaStream_t st, BodySoA soa, oon_body_f32* aos, uint32_t first, uint32_t count);
 
+// Emitter::emit_particles: up to n new bodies appended at index *d_n (which is advanced); *emitted_out = how many.
+int launch_emit(cudaStream_t st, BodySoA soa, uint32_t* d_n, uint32_t emitter, uint32_t n, const oon_emitter_cfg& cfg,
+                const float2* nozzles, unsigned long long seed, uint32_t* emitted_out);
+
 // slot order: identity, or Hilbert-curve order of the positions (FAST all-pairs mode)
 size_t order_temp_bytes(uint32_t slots);
 int launch_order_identity(cudaStream_t st, uint32_t* inv, uint32_t slots);

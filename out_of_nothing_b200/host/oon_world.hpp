@@ -124,6 +124,17 @@ public:
     // One model frame of OONApp::updates_for_next_frame (OON.cpp:1085-1095): the three updates + the expired-body sweep.
     void update(DeltaT dt, unsigned frames = 1) { push(); check(oon_step(h_, dt, frames)); device_ahead_ = true; }
 
+    // Emitter::emit_particles (Emitter.cpp:22-92) on the device: no upload, the host copy is refreshed lazily.
+    // `seed` replaces the reference's unseeded rand() stream (include/oon_gpu.h, oon_emit_particles).
+    unsigned emit_particles(EntityID emitter, unsigned n, oon_emitter_cfg const& cfg, uint64_t seed, float const* nozzles_xy = nullptr) {
+        push();
+        uint32_t emitted = 0;
+        check(oon_emit_particles(h_, emitter, n, &cfg, nozzles_xy, seed, &emitted));
+        if (emitted || !cfg.create_mass) device_ahead_ = true;
+        return emitted;
+    }
+    static oon_emitter_cfg emitter_defaults() { oon_emitter_cfg c{}; oon_emitter_cfg_default(&c); return c; }   // Emitter::Config{}
+
     // What the renderer reads every frame: x, y, r per body (OONMainDisplay_sfml.cpp:181-211), without a full download.
     std::vector<float> const& render_xyr() {
         push();

@@ -14,7 +14,7 @@ from typing import Optional
 import numpy as np
 
 from . import capi
-from .capi import BODY_F32, Events, OonError, Props
+from .capi import BODY_F32, EmitterCfg, Events, OonError, Props
 
 
 class Properties:
@@ -210,6 +210,32 @@ class World:
         ms = ctypes.c_float()
         self._check(self._L.oon_timer_stop(self._h, ctypes.byref(ms)))
         return ms.value
+
+    def emitter_config(self, **kw) -> EmitterCfg:
+        """``Emitter::Config`` with the reference's defaults (Emitter.hpp:24-37), overridden by keyword."""
+        c = EmitterCfg()
+        self._check(self._L.oon_emitter_cfg_default(ctypes.byref(c)))
+        for k, v in kw.items():
+            if k in ("eject_velocity", "eject_offset", "position_divergence"):
+                setattr(c, k + "_x", v[0]); setattr(c, k + "_y", v[1])
+            elif k in ("create_mass", "color"):
+                setattr(c, k, int(v))
+            else:
+                if not hasattr(c, k):
+                    raise AttributeError(k)
+                setattr(c, k, v)
+        return c
+
+    def emit_particles(self, emitter_id: int, n: int, cfg: EmitterCfg, nozzles=None, seed: int = 0) -> int:
+        """``Emitter::emit_particles`` (Emitter.cpp:22-92) on the device; returns the number of particles appended."""
+        nz = None
+        if nozzles is not None:
+            nz = np.ascontiguousarray(nozzles, np.float32)
+            assert nz.shape == (n, 2)
+        out = ctypes.c_uint32()
+        self._check(self._L.oon_emit_particles(self._h, emitter_id, n, ctypes.byref(cfg), nz.ctypes.data if nz is not None else None,
+                                               seed, ctypes.byref(out)))
+        return out.value
 
     def exchange_kind(self) -> str:
         """How a sharded world moves its exchange tiles: 'none' (one GPU), 'nccl_allgather' or 'peer_stores' (NVLink peer memory)."""
