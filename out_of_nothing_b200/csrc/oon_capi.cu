@@ -603,6 +603,13 @@ int start_order_ahead(oon_world* w, const StepParams& sp) {
 int do_intrinsic_pack(oon_world* w, const StepParams& sp, bool intrinsic, Prof* prof) {
     int rc = ensure_order(w, sp, prof);
     if (rc) return rc;
+    // The order of the NEXT frame is started here, before this frame's pack and interact kernels are even launched: its
+    // CTAs (one per canonical block, a whole SM's registers each) are placed while the GPU is still empty.  Started
+    // after the interact kernel they had to wait for an SM to drain (up to one long CTA, ~0.2 ms), and on a 1/8 shard
+    // the order then arrived after the interact kernel had finished (measured: +50 us per frame).  The order kernels
+    // read p, v, lifetime and the last kick — nothing this frame's pack writes except the player's velocity, which
+    // they therefore ignore (order_position).
+    if ((rc = start_order_ahead(w, sp))) return rc;
     PackOut out;
     if ((rc = begin_pack(w, out))) return rc;
     rc = timed(w, prof, 1, [&](int& launched) -> int {
@@ -615,7 +622,7 @@ int do_intrinsic_pack(oon_world* w, const StepParams& sp, bool intrinsic, Prof* 
     rc = exchange(w, prof);
     if (rc) return rc;
     w->tiles_fresh = true;
-    return start_order_ahead(w, sp);
+    return OON_OK;
 }
 
 int do_interact(oon_world* w, const StepParams& sp, Prof* prof) {
