@@ -64,7 +64,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -72,14 +72,27 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
 
-    def stop(self) -> dict:
+    def wait_for_samples(self, n: int, timeout_s: float = 8.0):
+        """nvidia-smi needs a second or so to come up on an 8-GPU box: do not start the load before it reports."""
+        t0 = time.perf_counter()
+        want = len(self.rows) + n
+        while self.proc and len(self.rows) < want and time.perf_counter() - t0 < timeout_s:
+            time.sleep(0.01)
+
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t_begin: float = 0.0, t_end: float = 1e30) -> dict:
+        """Summary of the samples taken under load: from the start of the warm-up (t_begin) to the end of the timed region."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.wait_for_samples(1, 0.5)                      # one more sample right after the timed region
         self.proc.terminate()
         sm, mx, reasons, power = [], [], set(), []
-        for row in self.rows:
+        rows = [r for t, r in self.rows if t_begin <= t <= t_end + 0.06] or [r for _, r in self.rows[-2:]]
+        for row in rows:
             f = [x.strip() for x in row.split(",")]
             if len(f) < 9:
                 continue
@@ -199,6 +212,8 @@ def main():
     # ---- warm-up (the clock sampler starts here so that short timed regions still get samples under load)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.wait_for_samples(1)
+    t_load0 = sampler.mark()
     w.step(dt, max(args.warmup, 3))
     w.synchronize()
     n_start = w.entity_count()
@@ -213,7 +228,7 @@ def main():
         ms = w.bench_frames(dt, args.steps, flush_bytes)
     barrier()
     host_s = time.perf_counter() - t_host0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_load0, time.perf_counter())
     launches = w.launch_count() - launches0
     ms = max_over_ranks(ms)
     n_end = w.entity_count()
