@@ -638,17 +638,9 @@ int do_interact(oon_world* w, const StepParams& sp, Prof* prof) {
         w->acc_dirty = true;
     } else if ((rc = ensure_partial(w))) return rc;
     const ExchangeView xv = xview(w);
-    const float* tiles_in = w->tiles;
-    if (getenv("OON_DEBUG_COPY_TILES") && !w->p2p) {       // experiment: does it matter that the peers wrote the buffer?
-        static float* copy = nullptr; static size_t cap = 0;
-        const size_t bytes = size_t(total_tiles(w)) * TILE_BYTES;
-        if (cap < bytes) { cudaFree(copy); cudaMalloc(&copy, bytes); cap = bytes; }
-        CU(w, cudaMemcpyAsync(copy, w->tiles, bytes, cudaMemcpyDeviceToDevice, w->stream));
-        tiles_in = copy;
-    }
     rc = timed(w, prof, 0, [&](int& launched) -> int {
         if (sp.n2n)
-            launched = launch_interact(w->stream, tiles_in, total_tiles(w), group_tiles, gpc, y_big, uint32_t(w->rank) * w->block, w->block,
+            launched = launch_interact(w->stream, w->tiles, total_tiles(w), group_tiles, gpc, y_big, uint32_t(w->rank) * w->block, w->block,
                                        w->d_n, w->soa[w->cur].d, uint32_t(w->rank) * w->block, sp, xv, w->acc, w->touch, w->fx_scale, w->partial,
                                        w->counters, w->cap, w->dbg_fraction, w->dbg_part);
         else
@@ -964,22 +956,30 @@ int oon_upload(oon_world* w, const oon_body_f32* bodies, uint64_t n) {
     CHECK_W(w);
     { int qrc = quiesce_aux(w); if (qrc) return qrc; }
     if (n && !bodies) return fail(w, OON_ERR_INVALID, "null body table");
+    // Does any body have a finite lifetime (then the frames include the sweep and keep the identity order)?  A sharded
+    // world must know before it accepts the table (every rank sees the whole table); a single-GPU world lets the unpack
+    // kernel find out — walking 60-byte records on the host cost more than the PCIe copy of the same table.
     bool mortals = false;
-    for (uint64_t i = 0; i < n; ++i) mortals |= mortal(bodies[i].lifetime);
-    if (mortals && w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "bodies with finite lifetimes on a sharded world are not implemented in this build");
+    if (w->nranks > 1) {
+        for (uint64_t i = 0; i < n; ++i) mortals |= mortal(bodies[i].lifetime);
+        if (mortals) return fail(w, OON_ERR_UNSUPPORTED, "bodies with finite lifetimes on a sharded world are not implemented in this build");
+    }
     int rc = layout(w, n, 0);
     if (rc) return rc;
-    w->has_mortals = mortals;
     const uint64_t lo = uint64_t(w->rank) * w->block;
+    CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));     // doubles as the unpack kernel's "mortal seen" flag
     if (w->n_local) {
         if ((rc = ensure_aos(w, w->n_local))) return rc;
         CU(w, cudaMemcpyAsync(w->aos_dev, bodies + lo, size_t(w->n_local) * sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
-        w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, 0, w->n_local);
+        w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, 0, w->n_local, w->d_removed_count);
         CU(w, cudaGetLastError());
     }
     CU(w, cudaMemcpyAsync(w->d_n, &w->n_local, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+    uint32_t seen = 0;
+    CU(w, cudaMemcpyAsync(&seen, w->d_removed_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
     CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));
     CU(w, cudaStreamSynchronize(w->stream));     // the caller may reuse `bodies` immediately (pageable memory)
+    w->has_mortals = mortals || seen != 0;
     return OON_OK;
 }
 
@@ -1096,7 +1096,7 @@ int oon_add_bodies(oon_world* w, const oon_body_f32* bodies, uint64_t k) {
     if ((rc = ensure_aos(w, k))) return rc;
     for (uint64_t i = 0; i < k; ++i) w->has_mortals |= mortal(bodies[i].lifetime);
     CU(w, cudaMemcpyAsync(w->aos_dev, bodies, size_t(k) * sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
-    w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, old_n, uint32_t(k));
+    w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, old_n, uint32_t(k), nullptr);
     CU(w, cudaGetLastError());
     CU(w, cudaMemcpyAsync(w->d_n, &w->n_local, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
     CU(w, cudaStreamSynchronize(w->stream));
@@ -1175,7 +1175,7 @@ int oon_set_body(oon_world* w, uint64_t ndx, const oon_body_f32* in) {
     if ((rc = ensure_aos(w, 1))) return rc;
     w->has_mortals |= mortal(in->lifetime);
     CU(w, cudaMemcpyAsync(w->aos_dev, in, sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
-    w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, uint32_t(ndx), 1);
+    w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, uint32_t(ndx), 1, nullptr);
     CU(w, cudaGetLastError());
     CU(w, cudaStreamSynchronize(w->stream));
     w->tiles_fresh = false;

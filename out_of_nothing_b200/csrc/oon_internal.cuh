@@ -118,7 +118,8 @@ constexpr int FX_MAX_SHIFT = 96;     // 24-bit mantissa << 96 = 120 bits
 // `inv` maps a local slot of the exchange buffer to the local body stored there (identity unless sorted).
 
 // AoS (60 B records) <-> SoA
-int launch_unpack_f32(cudaStream_t st, const oon_body_f32* aos, BodySoA soa, uint32_t first, uint32_t count);
+// mortal_seen (optional): set to 1 if any unpacked body has a finite lifetime
+int launch_unpack_f32(cudaStream_t st, const oon_body_f32* aos, BodySoA soa, uint32_t first, uint32_t count, uint32_t* mortal_seen);
 int launch_pack_f32(cudaStream_t st, BodySoA soa, oon_body_f32* aos, uint32_t first, uint32_t count);
 
 // Emitter::emit_particles: up to n new bodies appended at index *d_n (which is advanced); *emitted_out = how many.
