@@ -105,7 +105,8 @@ struct oon_world {
     void* ipc_stage = nullptr;                           // device staging for the handle exchange
     float* peer_tiles[2][8] = {};                        // peers' exchange buffers (imported), indexed by rank
     uint32_t* peer_flags[8] = {};                        // peers' flag arrays (imported)
-    uint32_t group_tiles_override = 0, debug_gpc = 0, tail_waves_x2 = 6;
+    uint32_t group_tiles_override = 0, debug_gpc = 0, debug_spc = 0, tail_waves_x2 = 4;
+    int small_tiles_override = -1;
     uint32_t dbg_fraction = 0, dbg_part = 0;             // oon_debug_time_interact: launch a part of the target blocks
     float4* scratch4 = nullptr;                          // player-only reaction buffer, one float4 per slot
     size_t tiles_cap_slots = 0;                          // slots the exchange buffer (and scratch4) can hold
@@ -362,31 +363,43 @@ int layout(oon_world* w, uint64_t n_total, uint32_t keep) {
 
 uint32_t total_tiles(const oon_world* w) { return uint32_t(uint64_t(w->block) * w->nranks / TS); }
 
-// Canonical groups of source tiles: FP32 sums inside a group, exact sums across groups.  The group size is a function
-// of the world size only (it fixes the rounding of the result).  How the groups are dealt to CTAs is launch geometry
-// and free to choose: the bulk goes to CTAs that walk `gpc` groups (the first y_big rows of the grid), the last
-// ~3 waves' worth to CTAs of one group each, so that the SMs run dry together (a 1/8 shard of the 100k-body world is
-// only ~8 waves of uniform CTAs: 8.1 waves cost 9).
-void grouping(const oon_world* w, uint32_t& group_tiles, uint32_t& gpc, uint32_t& y_big) {
+// Canonical groups of source tiles: FP32 sums inside a group, exact sums across groups.  Group sizes are a function of
+// the world size only (they fix the rounding of the result): 4 tiles (2 below 128 tiles, 1 below 32), and from 128 tiles
+// on the last 32-35 tiles of the source range are groups of their own.  How the groups are dealt to CTAs is launch
+// geometry and free to choose: the bulk goes to CTAs that walk `gpc` groups (16 tiles), then about tail_waves waves of
+// one-group CTAs, then the single tiles — so that the SMs run dry together (a 1/8 shard of the 100k-body world is only
+// ~8 waves of uniform CTAs: 8.1 waves cost 9, and the drain after the last wave costs half a CTA's duration).
+InteractGeometry grouping(const oon_world* w) {
+    InteractGeometry geo{};
     const uint32_t ntiles = total_tiles(w);
-    group_tiles = ntiles >= 128 ? 4u : ntiles >= 32 ? 2u : 1u;
-    if (w->group_tiles_override) group_tiles = w->group_tiles_override;      // experiments only: changes the rounding
-    const uint64_t ngroups = (ntiles + group_tiles - 1) / group_tiles;
+    geo.group_tiles = ntiles >= 128 ? 4u : ntiles >= 32 ? 2u : 1u;
+    uint32_t n_small = ntiles >= 128 ? 32u : 0u;
+    if (w->group_tiles_override) geo.group_tiles = w->group_tiles_override;      // experiments only: changes the rounding
+    if (w->small_tiles_override >= 0) n_small = std::min<uint32_t>(uint32_t(w->small_tiles_override), ntiles);   // likewise
+    geo.small_begin = n_small ? (ntiles - n_small) / geo.group_tiles * geo.group_tiles : ntiles;
+    const uint64_t nbig = (uint64_t(geo.small_begin) + geo.group_tiles - 1) / geo.group_tiles;   // groups before small_begin
     uint64_t target_blocks = (uint64_t(w->block) + K1_TARGETS_PER_CTA - 1) / K1_TARGETS_PER_CTA;
     if (w->dbg_fraction > 1) target_blocks = (target_blocks + w->dbg_fraction - 1) / w->dbg_fraction;
     const uint64_t slots = uint64_t(w->sm_count) * 4;                         // resident CTAs
     // long CTAs: ~16 tiles, more for very large worlds (keep the grid below ~64 waves and gridDim.y below 65535)
-    uint64_t g = std::max<uint64_t>(1, 16 / group_tiles);
-    g = std::max<uint64_t>(g, (target_blocks * ngroups + slots * 64 - 1) / (slots * 64));
-    g = std::max<uint64_t>(g, (ngroups + 60000) / 60001);
+    uint64_t g = std::max<uint64_t>(1, 16 / geo.group_tiles);
+    g = std::max<uint64_t>(g, (target_blocks * nbig + slots * 64 - 1) / (slots * 64));
+    g = std::max<uint64_t>(g, (nbig + 50000) / 50001);
     if (w->debug_gpc) g = w->debug_gpc;                                        // tuning experiments only
-    g = std::min<uint64_t>(g, ngroups);
-    // short CTAs: the last rows of the grid, about tail_waves waves of them
-    uint64_t ys = g > 1 ? (slots * w->tail_waves_x2 / 2 + target_blocks - 1) / target_blocks : 0;
-    ys = std::min<uint64_t>(ys, std::min<uint64_t>(ngroups, 4000));
-    const uint64_t yb = (ngroups - ys) / g;
-    gpc = uint32_t(g);
-    y_big = uint32_t(yb);
+    g = std::max<uint64_t>(1, std::min<uint64_t>(g, std::max<uint64_t>(1, nbig)));
+    // one-group CTAs: about tail_waves_x2 / 2 waves of them
+    uint64_t ymid = g > 1 ? (slots * w->tail_waves_x2 / 2 + target_blocks - 1) / target_blocks : 0;
+    ymid = std::min<uint64_t>(ymid, std::min<uint64_t>(nbig, 4000));
+    const uint64_t yb = (nbig - ymid) / g;
+    geo.gpc = uint32_t(g);
+    geo.y_big = uint32_t(yb);
+    geo.y_mid = uint32_t(nbig - yb * g);
+    // single tiles: at least ~2.5 waves of CTAs, up to 4 tiles per CTA when there are many target blocks
+    const uint64_t n_single = ntiles - geo.small_begin;
+    uint64_t spc = n_single ? target_blocks * n_single * 2 / (slots * 5) : 1;
+    geo.spc = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>(spc, 4)));
+    if (w->debug_spc) geo.spc = w->debug_spc;
+    return geo;
 }
 
 int ensure_partial(oon_world* w) {
@@ -626,11 +639,11 @@ int do_intrinsic_pack(oon_world* w, const StepParams& sp, bool intrinsic, Prof* 
 }
 
 int do_interact(oon_world* w, const StepParams& sp, Prof* prof) {
-    uint32_t group_tiles = 1, gpc = 1, y_big = 0;
+    InteractGeometry geo{};
     const bool fast_n2n = sp.n2n && !sp.exact;
     int rc;
     if (fast_n2n) {
-        grouping(w, group_tiles, gpc, y_big);
+        geo = grouping(w);
         if (w->acc_dirty) {                                // only after a (re)allocation or a pass nobody integrated
             CU(w, cudaMemsetAsync(w->acc, 0, sizeof(unsigned long long) * 2 * FX_LIMBS * w->acc_cap, w->stream));
             CU(w, cudaMemsetAsync(w->touch, 0, sizeof(uint32_t) * w->acc_cap, w->stream));
@@ -640,7 +653,7 @@ int do_interact(oon_world* w, const StepParams& sp, Prof* prof) {
     const ExchangeView xv = xview(w);
     rc = timed(w, prof, 0, [&](int& launched) -> int {
         if (sp.n2n)
-            launched = launch_interact(w->stream, w->tiles, total_tiles(w), group_tiles, gpc, y_big, uint32_t(w->rank) * w->block, w->block,
+            launched = launch_interact(w->stream, w->tiles, total_tiles(w), geo, uint32_t(w->rank) * w->block, w->block,
                                        w->d_n, w->soa[w->cur].d, uint32_t(w->rank) * w->block, sp, xv, w->acc, w->touch, w->fx_scale, w->partial,
                                        w->counters, w->cap, w->dbg_fraction, w->dbg_part);
         else
@@ -847,6 +860,8 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
     if (const char* e = getenv("OON_MORTON")) w->morton_enabled = atoi(e) != 0;
     if (const char* e = getenv("OON_DEBUG_GPC")) w->debug_gpc = uint32_t(atoi(e));
     if (const char* e = getenv("OON_DEBUG_TAIL_X2")) w->tail_waves_x2 = uint32_t(atoi(e));
+    if (const char* e = getenv("OON_DEBUG_SPC")) w->debug_spc = uint32_t(atoi(e));
+    if (const char* e = getenv("OON_SMALL_TILES")) w->small_tiles_override = atoi(e);
     if (const char* e = getenv("OON_ASYNC_SORT")) w->async_sort = atoi(e) != 0;
     if (const char* e = getenv("OON_ORDER_ONE_CTA")) w->order_one_cta = atoi(e) != 0;
     if (const char* e = getenv("OON_MORTON_MIN")) { long v = atol(e); if (v >= 0) w->morton_min_bodies = uint64_t(v); }

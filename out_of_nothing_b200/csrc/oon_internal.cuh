@@ -143,13 +143,22 @@ int launch_order_block(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint32
 int launch_intrinsic_pack(cudaStream_t st, BodySoA soa, const uint32_t* inv, const uint32_t* d_n, uint32_t slots,
                           uint32_t body_base, const PackOut& out, StepParams sp, bool do_intrinsic, unsigned long long* counters);
 
+// How the source tiles of the FAST all-pairs pass are grouped (canonical: a function of the world size only, it fixes
+// the rounding) and how the groups are dealt to CTAs (launch geometry: free, the sums across groups are exact).
+struct InteractGeometry {
+    uint32_t group_tiles;    // canonical: tiles [0, small_begin) are summed in FP32 in groups of this many tiles ...
+    uint32_t small_begin;    // canonical: ... tiles [small_begin, ntiles) one by one (a multiple of group_tiles; ntiles if none)
+    uint32_t gpc;            // geometry: grid rows [0, y_big) walk gpc groups,
+    uint32_t y_big;
+    uint32_t y_mid;          // geometry: the next y_mid rows one group (y_big * gpc + y_mid == groups before small_begin),
+    uint32_t spc;            // geometry: the rows after them spc single tiles
+};
+
 // The all-pairs pass.  tiles: whole gathered buffer (ntiles tiles).  Targets = local slots [0, slots) living at
-// global slot target_base.  FAST: sources are cut in canonical groups of `group_tiles` tiles (a function of the
-// world size only); a CTA of the first y_big grid rows walks `gpc` consecutive groups, the CTAs after them one group
-// each (launch geometry, free: y_big * gpc <= number of groups); group sums go to
+// global slot target_base.  FAST: sources are cut in canonical groups and dealt to CTAs as `geo` says; group sums go to
 // acc [2 components][FX_LIMBS][slots] (64-bit integer atomics) and touch visits to touch[slots].
 // EXACT: partial[slots] = {new v.x, new v.y, touch visits, -}.
-int launch_interact(cudaStream_t st, const float* tiles, uint32_t ntiles, uint32_t group_tiles, uint32_t gpc, uint32_t y_big,
+int launch_interact(cudaStream_t st, const float* tiles, uint32_t ntiles, const InteractGeometry& geo,
                     uint32_t target_base, uint32_t slots, const uint32_t* d_n_local, BodySoA soa, uint32_t body_base,
                     StepParams sp, const ExchangeView& xv, unsigned long long* acc, uint32_t* touch, int* fx_scale, float4* partial,
                     unsigned long long* counters, CaptureBuf cap, uint32_t dbg_fraction = 0, uint32_t dbg_part = 0);

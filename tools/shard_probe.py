@@ -20,8 +20,10 @@ fracs = [int(x) for x in os.environ.get("PROBE_FRAC", "1,2,4,8").split(",")]
 frames = int(os.environ.get("PROBE_FRAMES", "12"))
 for group in (int(x) for x in os.environ.get("PROBE_GROUP", "0").split(",")):
     for gpc in (int(x) for x in os.environ.get("PROBE_GPC", "0").split(",")):
-        for tail in (int(x) for x in os.environ.get("PROBE_TAIL", "3").split(",")):
+        for tail, small in ((int(x), int(y)) for x in os.environ.get("PROBE_TAIL", "6").split(",") for y in os.environ.get("PROBE_SMALL", "-1").split(",")):
             os.environ.pop("OON_GROUP_TILES", None)
+            os.environ.pop("OON_SMALL_TILES", None)
+            if small >= 0: os.environ["OON_SMALL_TILES"] = str(small)
             if group: os.environ["OON_GROUP_TILES"] = str(group)
             os.environ["OON_DEBUG_GPC"] = str(gpc)
             os.environ["OON_DEBUG_TAIL_X2"] = str(tail)
@@ -33,6 +35,6 @@ for group in (int(x) for x in os.environ.get("PROBE_GROUP", "0").split(",")):
                 for f in fracs:
                     acc[f].append(w.debug_time_interact(dt, f, k % f))
                 w.update_pairwise(dt); w.update_global(dt)
-            print("group_tiles %d gpc %2d tail_x2 %d: " % (group, gpc, tail) +
+            print("group_tiles %d gpc %2d tail_x2 %d small %3d: " % (group, gpc, tail, small) +
                   "  ".join("1/%d %.4f (x%d = %.3f)" % (f, sum(v) / len(v), f, f * sum(v) / len(v)) for f, v in acc.items()), flush=True)
             w.close()
