@@ -119,6 +119,9 @@ struct oon_world {
     uint32_t* removed_idx = nullptr; uint32_t removed_cap = 0;
     oon_body_f32* aos_dev = nullptr; size_t aos_cap = 0;   // staging for upload/download
     float* xyr_dev = nullptr; size_t xyr_cap = 0;
+    cudaStream_t copy_stream = nullptr;                     // render read-back beside the next frames (oon_download_render_begin/_end)
+    cudaEvent_t ev_render_ready = nullptr, ev_render_done = nullptr;
+    bool render_pending = false; uint64_t render_count = 0;
     CaptureBuf cap{};
 
     // slot order of the exchange buffer: inv[slot] = local body stored there
@@ -924,6 +927,7 @@ int oon_destroy(oon_world* w) {
     if (w->ev_main) cudaEventDestroy(w->ev_main);
     if (w->ev_sorted) cudaEventDestroy(w->ev_sorted);
     cudaFree(w->inv_next);
+    if (w->copy_stream) { cudaStreamSynchronize(w->copy_stream); cudaStreamDestroy(w->copy_stream); cudaEventDestroy(w->ev_render_ready); cudaEventDestroy(w->ev_render_done); }
     if (w->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(w->comm);
     soa_free(w->soa[0]); soa_free(w->soa[1]);
     cudaFree(w->tiles_buf[0]); cudaFree(w->tiles_buf[1]); cudaFree(w->acc); cudaFree(w->touch); cudaFree(w->fx_scale); cudaFree(w->rank_stats);
@@ -1066,17 +1070,25 @@ int oon_download_f64(oon_world* w, oon_body_f64* out, uint64_t capacity, uint64_
     return OON_OK;
 }
 
-int oon_download_render(oon_world* w, float* xyr, uint64_t capacity, uint64_t* n_out) {
-    CHECK_W(w);
+// Pack {x, y, r} of every body on the main stream (sharded: gather the ranks' blocks) and copy them to the host on the
+// copy stream; the main stream is free for the next frames as soon as the pack is enqueued.
+static int render_enqueue(oon_world* w, float* xyr, uint64_t capacity, uint64_t* n_out) {
     int rc = sync_count(w);
     if (rc) return rc;
     const uint64_t n = w->n_total;
     if (n_out) *n_out = n;
     if (n > capacity) return fail(w, OON_ERR_CAPACITY, "render download needs room for %llu bodies", (unsigned long long)n);
     if (n && !xyr) return fail(w, OON_ERR_INVALID, "null output");
+    if (!w->copy_stream) {
+        CU(w, cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
+        CU(w, cudaEventCreateWithFlags(&w->ev_render_ready, cudaEventDisableTiming));
+        CU(w, cudaEventCreateWithFlags(&w->ev_render_done, cudaEventDisableTiming));
+    }
+    if (w->render_pending) CU(w, cudaStreamWaitEvent(w->stream, w->ev_render_done, 0));   // the staging buffer is still being read
     const size_t per = size_t(w->block) * 3;
     const size_t need = per * w->nranks;
     if (need > w->xyr_cap) {
+        if (w->render_pending) CU(w, cudaEventSynchronize(w->ev_render_done));
         cudaFree(w->xyr_dev); w->xyr_dev = nullptr; w->xyr_cap = 0;
         if ((rc = dev_alloc(w, &w->xyr_dev, need + need / 2))) return rc;
         w->xyr_cap = need + need / 2;
@@ -1084,8 +1096,35 @@ int oon_download_render(oon_world* w, float* xyr, uint64_t capacity, uint64_t* n
     w->launches += launch_render_pack(w->stream, w->soa[w->cur].d, w->d_n, w->block, w->xyr_dev + per * w->rank);
     CU(w, cudaGetLastError());
     if (w->nranks > 1) NC(w, g_nccl.AllGather(w->xyr_dev + per * w->rank, w->xyr_dev, per, ncclFloat, w->comm, w->stream));
-    if (n) CU(w, cudaMemcpyAsync(xyr, w->xyr_dev, size_t(n) * 3 * sizeof(float), cudaMemcpyDeviceToHost, w->stream));
-    CU(w, cudaStreamSynchronize(w->stream));
+    CU(w, cudaEventRecord(w->ev_render_ready, w->stream));
+    CU(w, cudaStreamWaitEvent(w->copy_stream, w->ev_render_ready, 0));
+    if (n) CU(w, cudaMemcpyAsync(xyr, w->xyr_dev, size_t(n) * 3 * sizeof(float), cudaMemcpyDeviceToHost, w->copy_stream));
+    CU(w, cudaEventRecord(w->ev_render_done, w->copy_stream));
+    w->render_pending = true;
+    w->render_count = n;
+    return OON_OK;
+}
+
+int oon_download_render(oon_world* w, float* xyr, uint64_t capacity, uint64_t* n_out) {
+    CHECK_W(w);
+    int rc = render_enqueue(w, xyr, capacity, n_out);
+    if (rc) return rc;
+    CU(w, cudaEventSynchronize(w->ev_render_done));
+    w->render_pending = false;
+    return OON_OK;
+}
+
+int oon_download_render_begin(oon_world* w, float* xyr_pinned, uint64_t capacity) {
+    CHECK_W(w);
+    return render_enqueue(w, xyr_pinned, capacity, nullptr);
+}
+
+int oon_download_render_end(oon_world* w, uint64_t* n_out) {
+    CHECK_W(w);
+    if (!w->render_pending) return fail(w, OON_ERR_INVALID, "oon_download_render_end without oon_download_render_begin");
+    CU(w, cudaEventSynchronize(w->ev_render_done));
+    w->render_pending = false;
+    if (n_out) *n_out = w->render_count;
     return OON_OK;
 }
 

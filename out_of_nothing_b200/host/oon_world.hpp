@@ -145,6 +145,11 @@ public:
         xyr_.resize(size_t(n) * 3);
         return xyr_;
     }
+    // The same read-back beside the simulation: begin() after update(), draw the previous frame, end().
+    // `pinned` = cudaHostAlloc'ed / cudaHostRegister'ed memory for 3 floats per body, valid until render_end().
+    void render_begin(float* pinned, size_t capacity_bodies) { push(); check(oon_download_render_begin(h_, pinned, capacity_bodies)); }
+    size_t render_end() { uint64_t n = 0; check(oon_download_render_end(h_, &n)); return size_t(n); }
+
     oon_events drain_events() { oon_events ev{}; check(oon_drain_events(h_, &ev)); return ev; }
 
     // ---- persistence (World_SaveLoad.cpp) --------------------------------------------------------

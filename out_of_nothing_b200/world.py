@@ -133,6 +133,16 @@ class World:
         self._check(self._L.oon_download_render(self._h, out.ctypes.data, n, ctypes.byref(got)))
         return out[: got.value]
 
+    def download_render_begin(self, ptr: int, capacity: int):
+        """Start the render read-back ({x, y, r} per body) into pinned host memory at ``ptr``; returns at once."""
+        self._check(self._L.oon_download_render_begin(self._h, ptr, capacity))
+
+    def download_render_end(self) -> int:
+        """Wait for the read-back started by download_render_begin; returns the number of bodies it holds."""
+        n = ctypes.c_uint64()
+        self._check(self._L.oon_download_render_end(self._h, ctypes.byref(n)))
+        return n.value
+
     def entity_count(self) -> int:
         n = ctypes.c_uint64()
         self._check(self._L.oon_body_count(self._h, ctypes.byref(n)))

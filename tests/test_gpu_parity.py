@@ -578,3 +578,26 @@ def test_extreme_mass_ratio_keeps_the_small_kicks():
     # body 0 feels only the light ones: compare it on its own scale
     e0 = np.sqrt(((kick[0] - truth[0]) ** 2).sum()) / np.sqrt((truth[0] ** 2).sum())
     assert e0 <= 10 * TOL_KICK_MAX, e0
+
+
+# ---------------------------------------------------------------------------------------------- render sync (row f4)
+def test_render_readback_runs_beside_the_next_frames(kat1):
+    """oon_download_render_begin/_end: the positions of frame k reach pinned host memory while frames k+1.. are computed."""
+    import torch
+    start, _ = kat1
+    w = gpu_world(start.bodies, smoke_props(start), FAST, capture=0)
+    n = w.entity_count()
+    pinned = torch.empty(n * 3, dtype=torch.float32).pin_memory()
+    w.step(DT, 2)
+    ref_k = w.download_render()                              # synchronous read-back of frame 2
+    w.download_render_begin(pinned.data_ptr(), n)            # asynchronous read-back of the same frame ...
+    w.step(DT, 5)                                            # ... while five more frames are enqueued
+    assert w.download_render_end() == n
+    assert pinned.numpy().reshape(n, 3).tobytes() == ref_k.tobytes()
+    later = w.download_render()
+    assert later.tobytes() != ref_k.tobytes()                # the world did move on
+    full = w.download()
+    assert (later[:, :2] == full["p"]).all() and (later[:, 2] == full["r"]).all()
+    with pytest.raises(capi.OonError):
+        w.download_render_end()                              # nothing in flight
+    w.close()
