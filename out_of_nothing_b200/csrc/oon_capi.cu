@@ -113,6 +113,9 @@ struct oon_world {
     float2* kick = nullptr; uint32_t kick_cap = 0; bool kick_valid = false;
     uint32_t* d_n = nullptr;  // live local bodies (device)
     uint32_t* d_removed_count = nullptr;
+    int* runinfo = nullptr;                              // sharded sweep: [nranks][4] {bodies, trailing expired run, whole block one run, -}
+    uint32_t* d_counts = nullptr;                        // sharded: live bodies of every rank (device), counts[] = host copy
+    std::vector<uint32_t> counts;
     unsigned long long* counters = nullptr;   // C_COUNT
     void* sweep_temp = nullptr; size_t sweep_temp_bytes = 0;
     int* sweep_scratch = nullptr; uint32_t sweep_scratch_cap = 0;
@@ -710,7 +713,9 @@ int do_integrate(oon_world* w, const StepParams& sp, bool apply_pairwise, bool d
 }
 
 int do_sweep(oon_world* w, uint32_t player_ndx, Prof* prof) {
-    if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "expired-body sweep on a sharded world is not implemented in this build");
+    // Sharded: every rank compacts its own index block (blocks become ragged: fewer bodies than slots); the one thing that
+    // crosses ranks is the parity of a run of expired bodies that spans a block boundary.  The player must live on rank 0.
+    if (w->nranks > 1 && player_ndx >= w->block) return fail(w, OON_ERR_UNSUPPORTED, "sweep on a sharded world: the player must be on rank 0");
     const uint32_t slots = w->block;
     SoAStorage& other = w->soa[w->cur ^ 1];
     if (other.cap < w->soa[w->cur].cap) { int rc = soa_alloc(w, other, w->soa[w->cur].cap); if (rc) return rc; }
@@ -729,10 +734,19 @@ int do_sweep(oon_world* w, uint32_t player_ndx, Prof* prof) {
         int rc = dev_alloc(w, &w->removed_idx, w->soa[w->cur].cap); if (rc) return rc;
         w->removed_cap = w->soa[w->cur].cap;
     }
+    const uint32_t first_tested = w->rank == 0 ? player_ndx + 1 : 0u;
     int rc = timed(w, prof, 3, [&](int& launched) -> int {
         CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));
-        launched = launch_sweep(w->stream, w->soa[w->cur].d, other.d, w->d_n, slots, player_ndx, w->sweep_temp, w->sweep_temp_bytes,
-                                w->sweep_scratch, w->removed_idx, w->removed_cap, w->d_removed_count, w->counters);
+        launched = launch_sweep_scan(w->stream, w->soa[w->cur].d, w->d_n, slots, first_tested, w->sweep_temp, w->sweep_temp_bytes,
+                                     w->sweep_scratch, w->nranks > 1 ? w->runinfo + 4 * w->rank : nullptr);
+        CU(w, cudaGetLastError());
+        if (w->nranks > 1) {
+            NC(w, g_nccl.AllGather(w->runinfo + 4 * w->rank, w->runinfo, 4, ncclInt32, w->comm, w->stream));
+            ++launched;
+        }
+        launched += launch_sweep_compact(w->stream, w->soa[w->cur].d, other.d, w->d_n, slots, w->nranks > 1 ? w->runinfo : nullptr, w->rank,
+                                         w->sweep_temp, w->sweep_temp_bytes, w->sweep_scratch, w->removed_idx, w->removed_cap,
+                                         w->d_removed_count, w->counters);
         CU(w, cudaGetLastError());
         return OON_OK;
     });
@@ -745,13 +759,32 @@ int do_sweep(oon_world* w, uint32_t player_ndx, Prof* prof) {
 
 // Refresh the host's idea of the body count after device-side removals.
 int sync_count(oon_world* w) {
-    if (!w->has_mortals || w->nranks > 1) return OON_OK;
-    uint32_t n = 0;
-    CU(w, cudaMemcpyAsync(&n, w->d_n, sizeof n, cudaMemcpyDeviceToHost, w->stream));
+    if (!w->has_mortals) return OON_OK;
+    if (w->nranks == 1) {
+        uint32_t n = 0;
+        CU(w, cudaMemcpyAsync(&n, w->d_n, sizeof n, cudaMemcpyDeviceToHost, w->stream));
+        CU(w, cudaStreamSynchronize(w->stream));
+        w->n_local = n;
+        w->n_total = n;
+        return OON_OK;
+    }
+    // sharded: the ranks' blocks are ragged after a sweep — everybody learns everybody's count
+    CU(w, cudaMemcpyAsync(w->d_counts + w->rank, w->d_n, sizeof(uint32_t), cudaMemcpyDeviceToDevice, w->stream));
+    NC(w, g_nccl.AllGather(w->d_counts + w->rank, w->d_counts, 1, ncclUint32, w->comm, w->stream));
+    CU(w, cudaMemcpyAsync(w->counts.data(), w->d_counts, sizeof(uint32_t) * size_t(w->nranks), cudaMemcpyDeviceToHost, w->stream));
     CU(w, cudaStreamSynchronize(w->stream));
-    w->n_local = n;
-    w->n_total = n;
+    w->n_local = w->counts[size_t(w->rank)];
+    uint64_t total = 0;
+    for (uint32_t c : w->counts) total += c;
+    w->n_total = total;
     return OON_OK;
+}
+
+// Bodies of rank g as the host last learnt them: the even split after an upload, the gathered counts once bodies can expire.
+uint32_t rank_count(const oon_world* w, int g) {
+    if (w->nranks > 1 && w->has_mortals && !w->counts.empty()) return w->counts[size_t(g)];
+    const uint64_t lo = uint64_t(g) * w->block;
+    return w->n_total > lo ? uint32_t(std::min<uint64_t>(w->block, w->n_total - lo)) : 0u;
 }
 
 int step_impl(oon_world* w, float dt, uint32_t nsteps, Prof* prof) {
@@ -894,6 +927,9 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
         CUB_(cudaMalloc(&w->flags, sizeof(uint32_t) * size_t(nranks))); CUB_(cudaMemset(w->flags, 0, sizeof(uint32_t) * size_t(nranks)));
         CUB_(cudaMalloc(&w->timeouts, sizeof(uint32_t))); CUB_(cudaMemset(w->timeouts, 0, sizeof(uint32_t)));
         CUB_(cudaMalloc(&w->ipc_stage, 256 * size_t(nranks)));
+        CUB_(cudaMalloc(&w->runinfo, sizeof(int) * 4 * size_t(nranks))); CUB_(cudaMemset(w->runinfo, 0, sizeof(int) * 4 * size_t(nranks)));
+        CUB_(cudaMalloc(&w->d_counts, sizeof(uint32_t) * size_t(nranks)));
+        w->counts.assign(size_t(nranks), 0u);
     }
 #undef CUB_
     if (nranks > 1) {
@@ -931,7 +967,7 @@ int oon_destroy(oon_world* w) {
     if (w->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(w->comm);
     soa_free(w->soa[0]); soa_free(w->soa[1]);
     cudaFree(w->tiles_buf[0]); cudaFree(w->tiles_buf[1]); cudaFree(w->acc); cudaFree(w->touch); cudaFree(w->fx_scale); cudaFree(w->rank_stats);
-    cudaFree(w->flags); cudaFree(w->timeouts); cudaFree(w->ipc_stage); cudaFree(w->partial); cudaFree(w->scratch4); cudaFree(w->kick); cudaFree(w->d_n); cudaFree(w->d_removed_count);
+    cudaFree(w->flags); cudaFree(w->timeouts); cudaFree(w->ipc_stage); cudaFree(w->runinfo); cudaFree(w->d_counts); cudaFree(w->partial); cudaFree(w->scratch4); cudaFree(w->kick); cudaFree(w->d_n); cudaFree(w->d_removed_count);
     cudaFree(w->counters); cudaFree(w->sweep_temp); cudaFree(w->sweep_scratch); cudaFree(w->removed_idx); cudaFree(w->aos_dev);
     cudaFree(w->xyr_dev); cudaFree(w->cap.coll); cudaFree(w->cap.touch);
     cudaFree(w->inv); cudaFree(w->order_temp); cudaFree(w->order_keys); cudaFree(w->order_vals); cudaFree(w->order_bounds);
@@ -979,10 +1015,8 @@ int oon_upload(oon_world* w, const oon_body_f32* bodies, uint64_t n) {
     // world must know before it accepts the table (every rank sees the whole table); a single-GPU world lets the unpack
     // kernel find out — walking 60-byte records on the host cost more than the PCIe copy of the same table.
     bool mortals = false;
-    if (w->nranks > 1) {
+    if (w->nranks > 1)
         for (uint64_t i = 0; i < n; ++i) mortals |= mortal(bodies[i].lifetime);
-        if (mortals) return fail(w, OON_ERR_UNSUPPORTED, "bodies with finite lifetimes on a sharded world are not implemented in this build");
-    }
     int rc = layout(w, n, 0);
     if (rc) return rc;
     const uint64_t lo = uint64_t(w->rank) * w->block;
@@ -999,6 +1033,10 @@ int oon_upload(oon_world* w, const oon_body_f32* bodies, uint64_t n) {
     CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));
     CU(w, cudaStreamSynchronize(w->stream));     // the caller may reuse `bodies` immediately (pageable memory)
     w->has_mortals = mortals || seen != 0;
+    for (int g = 0; g < w->nranks && !w->counts.empty(); ++g) {          // the even split, until a sweep makes the blocks ragged
+        const uint64_t glo = uint64_t(g) * w->block;
+        w->counts[size_t(g)] = n > glo ? uint32_t(std::min<uint64_t>(w->block, n - glo)) : 0u;
+    }
     return OON_OK;
 }
 
@@ -1046,7 +1084,13 @@ int oon_download(oon_world* w, oon_body_f32* out, uint64_t capacity, uint64_t* n
     if (n_out) *n_out = n;
     if (n > capacity) return fail(w, OON_ERR_CAPACITY, "download needs room for %llu bodies, got %llu", (unsigned long long)n, (unsigned long long)capacity);
     if (n && !out) return fail(w, OON_ERR_INVALID, "null output");
-    if (n) CU(w, cudaMemcpyAsync(out, w->aos_dev, size_t(n) * sizeof(oon_body_f32), cudaMemcpyDeviceToHost, w->stream));
+    // one copy per rank: after a sweep the ranks' blocks hold fewer bodies than slots
+    uint64_t at = 0;
+    for (int g = 0; g < w->nranks; ++g) {
+        const uint32_t c = w->nranks == 1 ? uint32_t(n) : rank_count(w, g);
+        if (c) CU(w, cudaMemcpyAsync(out + at, w->aos_dev + size_t(g) * w->block, size_t(c) * sizeof(oon_body_f32), cudaMemcpyDeviceToHost, w->stream));
+        at += c;
+    }
     CU(w, cudaStreamSynchronize(w->stream));
     return OON_OK;
 }
@@ -1098,7 +1142,12 @@ static int render_enqueue(oon_world* w, float* xyr, uint64_t capacity, uint64_t*
     if (w->nranks > 1) NC(w, g_nccl.AllGather(w->xyr_dev + per * w->rank, w->xyr_dev, per, ncclFloat, w->comm, w->stream));
     CU(w, cudaEventRecord(w->ev_render_ready, w->stream));
     CU(w, cudaStreamWaitEvent(w->copy_stream, w->ev_render_ready, 0));
-    if (n) CU(w, cudaMemcpyAsync(xyr, w->xyr_dev, size_t(n) * 3 * sizeof(float), cudaMemcpyDeviceToHost, w->copy_stream));
+    uint64_t at = 0;
+    for (int g = 0; g < w->nranks; ++g) {                  // one copy per rank (ragged blocks after a sweep)
+        const uint32_t c = w->nranks == 1 ? uint32_t(n) : rank_count(w, g);
+        if (c) CU(w, cudaMemcpyAsync(xyr + at * 3, w->xyr_dev + per * size_t(g), size_t(c) * 3 * sizeof(float), cudaMemcpyDeviceToHost, w->copy_stream));
+        at += c;
+    }
     CU(w, cudaEventRecord(w->ev_render_done, w->copy_stream));
     w->render_pending = true;
     w->render_count = n;

@@ -183,9 +183,16 @@ int launch_integrate(cudaStream_t st, BodySoA soa, const uint32_t* inv, const ui
 // The caller's expired-body sweep (OON.cpp:1089-1095) as a stable device compaction from `src` into `dst`.
 // d_n is updated in place.  removed_idx (optional, capacity removed_cap) gets the indices at removal time.
 size_t sweep_temp_bytes(uint32_t slots);
-int launch_sweep(cudaStream_t st, BodySoA src, BodySoA dst, uint32_t* d_n, uint32_t slots, uint32_t player_ndx,
-                 void* temp, size_t temp_bytes, int* scratch_i32 /* 3*slots ints */, uint32_t* removed_idx,
-                 uint32_t removed_cap, uint32_t* d_removed_count, unsigned long long* counters);
+// Two phases so that a sharded world can all-gather the ranks' run bookkeeping in between (a run of expired bodies may
+// cross the boundary between two ranks' index blocks): scan = flags + "last non-expired index" (+ this rank's triple
+// {bodies, expired run the block ends with, whole block is one run} into my_runinfo); compact = keep flags from the run
+// parity (runinfo = all ranks' triples, or nullptr), new indices, stable scatter, new count.  first_tested = first local
+// index the sweep looks at (player + 1 on the rank that owns the player, 0 on the ranks after it).
+int launch_sweep_scan(cudaStream_t st, BodySoA src, const uint32_t* d_n, uint32_t slots, uint32_t first_tested,
+                      void* temp, size_t temp_bytes, int* scratch_i32 /* 3*slots ints */, int* my_runinfo);
+int launch_sweep_compact(cudaStream_t st, BodySoA src, BodySoA dst, uint32_t* d_n, uint32_t slots, const int* runinfo, int rank,
+                         void* temp, size_t temp_bytes, int* scratch_i32, uint32_t* removed_idx, uint32_t removed_cap,
+                         uint32_t* d_removed_count, unsigned long long* counters);
 
 // render read set: {x, y, r} per body
 int launch_render_pack(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint32_t slots, float* xyr);

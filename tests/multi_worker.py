@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run(rank, nranks, nccl_id, bodies_path, out_path, mode, steps, dt, props, p2p=True, split_steps=False):
+def run(rank, nranks, nccl_id, bodies_path, out_path, mode, steps, dt, props, p2p=True, split_steps=False, last_frame_fast=False):
     os.environ["OON_P2P"] = "1" if p2p else "0"
     from out_of_nothing_b200 import capi
     from out_of_nothing_b200.world import World
@@ -22,6 +22,10 @@ def run(rank, nranks, nccl_id, bodies_path, out_path, mode, steps, dt, props, p2
             w.update_intrinsic(dt); w.update_pairwise(dt); w.update_global(dt)
             if k == steps // 2:
                 w.upload(w.download())
+    elif last_frame_fast:                # `steps` frames in the given mode, then one FAST frame from that (shared) state
+        w.step(dt, steps)
+        w.math_mode = capi.MATH_FAST
+        w.step(dt, 1)
     else:
         w.step(dt, steps)
     out = w.download()
@@ -29,7 +33,7 @@ def run(rank, nranks, nccl_id, bodies_path, out_path, mode, steps, dt, props, p2
     ev = w.drain_events()
     np.save(out_path % rank, out)
     np.save((out_path % rank) + ".xyr.npy", xyr)
-    np.save((out_path % rank) + ".ev.npy", np.array([ev["collisions"], ev["touches"]], np.int64))
+    np.save((out_path % rank) + ".ev.npy", np.array([ev["collisions"], ev["touches"], ev["terminated"], ev["removed"]], np.int64))
     with open((out_path % rank) + ".kind", "w") as f:
         f.write(w.exchange_kind())
     w.close()
