@@ -20,6 +20,7 @@
 //   /root/reference/src/app/model/Entity.hpp:25-98, Entity.cpp:14-26
 //   /root/reference/src/app/OON.cpp:1083-1095        the caller's expired-body sweep
 //   /root/reference/src/app/model/Emitter.hpp:24-37, Emitter.cpp:22-92   Emitter::Config, emit_particles
+//   /root/reference/src/app/OON.cpp:778-803, 842-861, 984-1029           add_random_body_near, spawn, chemtrail_burst
 //   (the reference draws from the C library's unseeded rand(); here every draw is oon_rand(seed, k), a
 //   counter-based stand-in with the MSVC RAND_MAX the reference ships with — see EmitterConfig below)
 //
@@ -359,6 +360,64 @@ public:
         }
         if (!cfg.create_mass) emitter.recalc();
         return emitted;
+    }
+
+    // OONApp::chemtrail_burst, OON.cpp:984-1029 (the appcfg values arrive through cfg: v_factor, offset_velo_factor =
+    // chemtrail_offset_factor, particle_lifetime, create_mass, particle_density, velocity_divergence = chemtrail_divergence,
+    // particle_mass_min/max = M_min/M_max).  6 draws per particle: mass, p.x, p.y, v.x, v.y, colour.
+    unsigned chemtrail_burst(size_t emitter_id, unsigned n, const EmitterConfig<Num>& cfg, uint64_t seed) {
+        const Num RM = Num(OON_RAND_MAX);
+        unsigned emitted = 0;
+        EntityT& emitter = *bodies[emitter_id];
+        const Num p_range = emitter.r * 5;
+        const Num v_range = Num(CFG_GLOBE_RADIUS) * cfg.velocity_divergence;
+        for (unsigned i = 0; i++ < n;) {
+            const uint64_t k = uint64_t(i - 1) * 6;
+            const Num particle_mass = cfg.particle_mass_min + (cfg.particle_mass_max - cfg.particle_mass_min) * float(oon_rand(seed, k)) / RM;
+            if (!cfg.create_mass && emitter.mass < particle_mass) continue;
+            EntityT e;
+            e.lifetime = cfg.particle_lifetime;
+            e.density = cfg.particle_density;
+            e.p = {(Num(oon_rand(seed, k + 1)) * p_range) / RM - p_range / 2 + emitter.p.x + emitter.v.x * cfg.offset_velo_factor,
+                   (Num(oon_rand(seed, k + 2)) * p_range) / RM - p_range / 2 + emitter.p.y + emitter.v.y * cfg.offset_velo_factor};
+            e.v = {(Num(oon_rand(seed, k + 3)) * v_range) / RM - v_range / 2 + emitter.v.x * cfg.v_factor,
+                   (Num(oon_rand(seed, k + 4)) * v_range) / RM - v_range / 2 + emitter.v.y * cfg.v_factor};
+            e.color = (uint32_t)(float)0xffffff * uint32_t(oon_rand(seed, k + 5));
+            e.mass = particle_mass;
+            add_body(e);
+            ++emitted;
+            if (!cfg.create_mass) emitter.mass -= particle_mass;
+        }
+        emitter.recalc();
+        return emitted;
+    }
+
+    // OONApp::add_random_body_near, OON.cpp:778-803.  7 draws from k0: p.x, p.y, v.x, v.y, colour, colour, mass.
+    size_t add_random_body_near(size_t base_id, uint64_t seed, uint64_t k0) {
+        const Num RM = Num(OON_RAND_MAX);
+        const Num p_range = Num(CFG_GLOBE_RADIUS * 30), v_range = Num(CFG_GLOBE_RADIUS * 10);
+        const EntityT base = *bodies[base_id];
+        const Num M_min = base.mass / 9, M_max = base.mass * 3;
+        EntityT e;
+        e.p = {(Num(oon_rand(seed, k0)) * p_range) / RM - p_range / 2 + base.p.x,
+               (Num(oon_rand(seed, k0 + 1)) * p_range) / RM - p_range / 2 + base.p.y};
+        e.v = {(Num(oon_rand(seed, k0 + 2)) * v_range) / RM - v_range / 2 + base.v.x * 0.05f,
+               (Num(oon_rand(seed, k0 + 3)) * v_range) / RM - v_range / 2 + base.v.y * 0.05f};
+        e.color = 0xffffff & (uint32_t(oon_rand(seed, k0 + 4)) * uint32_t(oon_rand(seed, k0 + 5)));
+        e.mass = M_min + (M_max - M_min) * float(oon_rand(seed, k0 + 6)) / RM;
+        return add_body(e);
+    }
+
+    // OONApp::spawn, OON.cpp:842-861: bodies near the PLAYER, temperature and velocity inherited from the parent.
+    void spawn(size_t parent_id, unsigned n, uint64_t seed, size_t player_id = 0) {
+        const EntityT parent = *bodies[parent_id];
+        for (unsigned i = 0; i < n; ++i) {
+            const size_t ndx = add_random_body_near(player_id, seed, uint64_t(i) * 7);
+            EntityT& newborn = *bodies[ndx];
+            newborn.lifetime = EntityT::Unlimited;
+            newborn.T = parent.T;
+            newborn.v = parent.v;
+        }
     }
 
     // One frame of OONApp::updates_for_next_frame's model part (OON.cpp:1085-1095).

@@ -185,7 +185,20 @@ double oracle_time_steps(void* p, float dt, uint32_t nsteps, int sweep) {
 // Emitter::emit_particles (Emitter.cpp:22-92).  cfg = 15 floats in the order of oon_emitter_cfg (include/oon_gpu.h):
 // eject_velocity.xy, eject_offset.xy, v_factor, offset_velo_factor, particle_lifetime, create_mass, particle_density,
 // position_divergence.xy, velocity_divergence, particle_mass_min, particle_mass_max, color (as uint32 bits).
+// kind: 0 Emitter::emit_particles, 1 OONApp::chemtrail_burst (same 15-float configuration)
+uint32_t oracle_emit_kind(void* p, int kind, uint64_t emitter_id, uint32_t n, const float* c, const float* nozzles, uint64_t seed);
 uint32_t oracle_emit_particles(void* p, uint64_t emitter_id, uint32_t n, const float* c, const float* nozzles, uint64_t seed) {
+    return oracle_emit_kind(p, 0, emitter_id, n, c, nozzles, seed);
+}
+uint32_t oracle_chemtrail_burst(void* p, uint64_t emitter_id, uint32_t n, const float* c, uint64_t seed) {
+    return oracle_emit_kind(p, 1, emitter_id, n, c, nullptr, seed);
+}
+void oracle_spawn(void* p, uint64_t parent_id, uint64_t player_id, uint32_t n, uint64_t seed) {
+    auto* h = static_cast<Handle*>(p);
+    if (h->is_double) { if (parent_id < h->wd.bodies.size() && player_id < h->wd.bodies.size()) h->wd.spawn(size_t(parent_id), n, seed, size_t(player_id)); }
+    else { if (parent_id < h->wf.bodies.size() && player_id < h->wf.bodies.size()) h->wf.spawn(size_t(parent_id), n, seed, size_t(player_id)); }
+}
+uint32_t oracle_emit_kind(void* p, int kind, uint64_t emitter_id, uint32_t n, const float* c, const float* nozzles, uint64_t seed) {
     auto* h = static_cast<Handle*>(p);
     auto run = [&](auto& w) -> uint32_t {
         using Num = std::decay_t<decltype(w.bodies[0]->r)>;
@@ -198,6 +211,7 @@ uint32_t oracle_emit_particles(void* p, uint64_t emitter_id, uint32_t n, const f
         uint32_t color; std::memcpy(&color, &c[14], 4); cfg.color = color;
         std::vector<V2<Num>> nz;
         if (nozzles) for (uint32_t i = 0; i < n; ++i) nz.push_back({Num(nozzles[2 * i]), Num(nozzles[2 * i + 1])});
+        if (kind == 1) return w.chemtrail_burst(size_t(emitter_id), n, cfg, seed);
         return w.emit_particles(size_t(emitter_id), n, cfg, nozzles ? nz.data() : nullptr, seed);
     };
     return h->is_double ? run(h->wd) : run(h->wf);

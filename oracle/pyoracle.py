@@ -65,6 +65,9 @@ def lib():
         L.oracle_radius_from_mass_and_density_f32.argtypes = [f32, f32]
         L.oracle_emit_particles.argtypes = [vp, u64, u32, vp, vp, u64]
         L.oracle_emit_particles.restype = u32
+        L.oracle_chemtrail_burst.argtypes = [vp, u64, u32, vp, u64]
+        L.oracle_chemtrail_burst.restype = u32
+        L.oracle_spawn.argtypes = [vp, u64, u64, u32, u64]
         L.oracle_rand.argtypes = [u64, u64]
         L.oracle_rand.restype = i32
         _lib = L
@@ -147,14 +150,27 @@ class OracleWorld:
                       "particle_lifetime", "create_mass", "particle_density", "position_divergence_x", "position_divergence_y",
                       "velocity_divergence", "particle_mass_min", "particle_mass_max", "color")
 
-    def emit_particles(self, emitter_id: int, n: int, cfg, nozzles=None, seed: int = 0) -> int:
-        """Emitter::emit_particles (Emitter.cpp:22-92); cfg = any object with the EMITTER_FIELDS attributes."""
+    def _emitter_floats(self, cfg) -> np.ndarray:
         c = np.zeros(15, np.float32)
         for i, name in enumerate(self.EMITTER_FIELDS[:14]):
             c[i] = float(getattr(cfg, name))
         c[14:15].view(np.uint32)[0] = int(getattr(cfg, "color"))
+        return c
+
+    def emit_particles(self, emitter_id: int, n: int, cfg, nozzles=None, seed: int = 0) -> int:
+        """Emitter::emit_particles (Emitter.cpp:22-92); cfg = any object with the EMITTER_FIELDS attributes."""
+        c = self._emitter_floats(cfg)
         nz = None if nozzles is None else np.ascontiguousarray(nozzles, np.float32)
         return int(lib().oracle_emit_particles(self._h, emitter_id, n, c.ctypes.data, nz.ctypes.data if nz is not None else None, seed))
+
+    def chemtrail_burst(self, emitter_id: int, n: int, cfg, seed: int = 0) -> int:
+        """OONApp::chemtrail_burst (OON.cpp:984-1029)."""
+        c = self._emitter_floats(cfg)
+        return int(lib().oracle_chemtrail_burst(self._h, emitter_id, n, c.ctypes.data, seed))
+
+    def spawn(self, parent_id: int, n: int, seed: int = 0, player_id: int = 0):
+        """OONApp::spawn (OON.cpp:842-861) over add_random_body_near (OON.cpp:778-803)."""
+        lib().oracle_spawn(self._h, parent_id, player_id, n, seed)
 
     def step(self, dt: float, nsteps: int = 1, sweep: bool = True):
         lib().oracle_step(self._h, dt, nsteps, int(sweep))

@@ -78,7 +78,7 @@ EXPORTS = [
     "oon_abi_version", "oon_create", "oon_nccl_unique_id", "oon_create_sharded", "oon_destroy", "oon_last_error",
     "oon_props_default", "oon_set_props", "oon_get_props", "oon_set_math_mode", "oon_get_math_mode",
     "oon_upload", "oon_upload_f64", "oon_download", "oon_download_f64", "oon_download_render", "oon_download_render_begin", "oon_download_render_end", "oon_body_count",
-    "oon_add_bodies", "oon_remove_body", "oon_get_body", "oon_set_body", "oon_emitter_cfg_default", "oon_emit_particles",
+    "oon_add_bodies", "oon_remove_body", "oon_get_body", "oon_set_body", "oon_emitter_cfg_default", "oon_emit_particles", "oon_chemtrail_burst", "oon_spawn",
     "oon_step", "oon_update_intrinsic", "oon_update_pairwise", "oon_update_global", "oon_sweep_expired",
     "oon_synchronize", "oon_drain_events",
     "oon_timer_start", "oon_timer_stop", "oon_step_profiled", "oon_bench_frames", "oon_bench_frames_profiled", "oon_launch_count", "oon_exchange_kind",
@@ -129,6 +129,8 @@ def load():
     L.oon_set_body.argtypes = [vp, u64, vp]
     L.oon_emitter_cfg_default.argtypes = [P(EmitterCfg)]
     L.oon_emit_particles.argtypes = [vp, u64, u32, P(EmitterCfg), vp, u64, P(u32)]
+    L.oon_chemtrail_burst.argtypes = [vp, u64, u32, P(EmitterCfg), u64, P(u32)]
+    L.oon_spawn.argtypes = [vp, u64, u64, u32, u64]
     L.oon_download_render_begin.argtypes = [vp, vp, u64]
     L.oon_download_render_end.argtypes = [vp, P(u64)]
     L.oon_step.argtypes = [vp, f32, u32]

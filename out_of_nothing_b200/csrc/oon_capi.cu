@@ -1220,16 +1220,17 @@ int oon_emitter_cfg_default(oon_emitter_cfg* out) {
     return OON_OK;
 }
 
-int oon_emit_particles(oon_world* w, uint64_t emitter_ndx, uint32_t n, const oon_emitter_cfg* cfg, const float* nozzles_xy,
-                       uint64_t seed, uint32_t* emitted_out) {
-    CHECK_W(w);
+// The reference's three body-creating loops share one device kernel (k_emit) and this host side.
+static int emit_common(oon_world* w, int kind, uint64_t base_ndx, uint64_t parent_ndx, uint32_t n, const oon_emitter_cfg* cfg,
+                       const float* nozzles_xy, uint64_t seed, uint32_t* emitted_out, const char* what) {
     { int qrc = quiesce_aux(w); if (qrc) return qrc; }
     if (emitted_out) *emitted_out = 0;
-    if (!cfg) return fail(w, OON_ERR_INVALID, "null emitter configuration");
-    if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "emit_particles on a sharded world is not implemented in this build");
+    if (!cfg) return fail(w, OON_ERR_INVALID, "%s: null configuration", what);
+    if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "%s on a sharded world is not implemented in this build", what);
     int rc = sync_count(w);
     if (rc) return rc;
-    if (emitter_ndx >= w->n_local) return fail(w, OON_ERR_INVALID, "emitter index %llu out of range (%u bodies)", (unsigned long long)emitter_ndx, w->n_local);
+    if (base_ndx >= w->n_local || parent_ndx >= w->n_local)
+        return fail(w, OON_ERR_INVALID, "%s: body index %llu out of range (%u bodies)", what, (unsigned long long)std::max(base_ndx, parent_ndx), w->n_local);
     if (!n) return OON_OK;
     const uint32_t old_n = w->n_local;
     if ((rc = layout(w, uint64_t(old_n) + n, old_n))) return rc;        // room for all n; the count is corrected below
@@ -1240,16 +1241,35 @@ int oon_emit_particles(oon_world* w, uint64_t emitter_ndx, uint32_t n, const oon
         CU(w, cudaMemcpyAsync(nozzles_dev, nozzles_xy, size_t(n) * sizeof(float2), cudaMemcpyHostToDevice, w->stream));
     }
     CU(w, cudaMemcpyAsync(w->d_n, &old_n, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
-    w->launches += uint64_t(launch_emit(w->stream, w->soa[w->cur].d, w->d_n, uint32_t(emitter_ndx), n, *cfg, nozzles_dev, seed, w->d_removed_count));
+    w->launches += uint64_t(launch_emit(w->stream, w->soa[w->cur].d, w->d_n, uint32_t(base_ndx), uint32_t(parent_ndx), n, *cfg, nozzles_dev, seed, kind,
+                                        w->d_removed_count));
     CU(w, cudaGetLastError());
     uint32_t emitted = 0;
     CU(w, cudaMemcpyAsync(&emitted, w->d_removed_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
     CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));
     CU(w, cudaStreamSynchronize(w->stream));
     if ((rc = layout(w, uint64_t(old_n) + emitted, old_n + emitted))) return rc;   // bookkeeping only: capacity is there
-    if (emitted) w->has_mortals |= mortal(cfg->particle_lifetime);
+    if (emitted && kind != EMIT_SPAWN) w->has_mortals |= mortal(cfg->particle_lifetime);
     if (emitted_out) *emitted_out = emitted;
     return OON_OK;
+}
+
+int oon_emit_particles(oon_world* w, uint64_t emitter_ndx, uint32_t n, const oon_emitter_cfg* cfg, const float* nozzles_xy,
+                       uint64_t seed, uint32_t* emitted_out) {
+    CHECK_W(w);
+    return emit_common(w, EMIT_PARTICLES, emitter_ndx, emitter_ndx, n, cfg, nozzles_xy, seed, emitted_out, "emit_particles");
+}
+
+int oon_chemtrail_burst(oon_world* w, uint64_t emitter_ndx, uint32_t n, const oon_emitter_cfg* cfg, uint64_t seed, uint32_t* emitted_out) {
+    CHECK_W(w);
+    return emit_common(w, EMIT_CHEMTRAIL, emitter_ndx, emitter_ndx, n, cfg, nullptr, seed, emitted_out, "chemtrail_burst");
+}
+
+int oon_spawn(oon_world* w, uint64_t parent_ndx, uint64_t player_ndx, uint32_t n, uint64_t seed) {
+    CHECK_W(w);
+    oon_emitter_cfg cfg;
+    oon_emitter_cfg_default(&cfg);                         // unused by the spawn loop except as a non-null argument
+    return emit_common(w, EMIT_SPAWN, player_ndx, parent_ndx, n, &cfg, nullptr, seed, nullptr, "spawn");
 }
 
 int oon_get_body(oon_world* w, uint64_t ndx, oon_body_f32* out) {

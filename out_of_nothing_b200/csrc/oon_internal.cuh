@@ -122,9 +122,12 @@ constexpr int FX_MAX_SHIFT = 96;     // 24-bit mantissa << 96 = 120 bits
 int launch_unpack_f32(cudaStream_t st, const oon_body_f32* aos, BodySoA soa, uint32_t first, uint32_t count, uint32_t* mortal_seen);
 int launch_pack_f32(cudaStream_t st, BodySoA soa, oon_body_f32* aos, uint32_t first, uint32_t count);
 
-// Emitter::emit_particles: up to n new bodies appended at index *d_n (which is advanced); *emitted_out = how many.
-int launch_emit(cudaStream_t st, BodySoA soa, uint32_t* d_n, uint32_t emitter, uint32_t n, const oon_emitter_cfg& cfg,
-                const float2* nozzles, unsigned long long seed, uint32_t* emitted_out);
+// The reference's three body-creating loops on the device: up to n new bodies appended at index *d_n (which is
+// advanced); *emitted_out = how many.  emitter = the body they are created around (spawn: the player), parent = the
+// body a spawned one inherits T and v from.
+enum { EMIT_PARTICLES = 0, EMIT_CHEMTRAIL = 1, EMIT_SPAWN = 2 };
+int launch_emit(cudaStream_t st, BodySoA soa, uint32_t* d_n, uint32_t emitter, uint32_t parent, uint32_t n, const oon_emitter_cfg& cfg,
+                const float2* nozzles, unsigned long long seed, int kind, uint32_t* emitted_out);
 
 // slot order: identity, or Hilbert-curve order of the positions (FAST all-pairs mode)
 size_t order_temp_bytes(uint32_t slots);

@@ -247,6 +247,16 @@ class World:
                                                seed, ctypes.byref(out)))
         return out.value
 
+    def chemtrail_burst(self, emitter_id: int, n: int, cfg: EmitterCfg, seed: int = 0) -> int:
+        """``OONApp::chemtrail_burst`` (OON.cpp:984-1029) on the device; returns the number of particles appended."""
+        out = ctypes.c_uint32()
+        self._check(self._L.oon_chemtrail_burst(self._h, emitter_id, n, ctypes.byref(cfg), seed, ctypes.byref(out)))
+        return out.value
+
+    def spawn(self, parent_id: int, n: int, seed: int = 0, player_id: int = 0):
+        """``OONApp::spawn`` (OON.cpp:842-861): n random bodies near the player, inheriting T and v from the parent."""
+        self._check(self._L.oon_spawn(self._h, parent_id, player_id, n, seed))
+
     def exchange_kind(self) -> str:
         """How a sharded world moves its exchange tiles: 'none' (one GPU), 'nccl_allgather' or 'peer_stores' (NVLink peer memory)."""
         k = ctypes.c_int()

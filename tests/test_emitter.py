@@ -145,3 +145,68 @@ def test_thrusting_player_scene_with_expiring_exhaust(mode):
             assert (got["T"] == ref["T"]).all() and (got["lifetime"] == ref["lifetime"]).all() and (got["r"] == ref["r"]).all()
     assert o.n > 1010 and w.drain_events()["removed"] > 50        # exhaust was created and swept
     w.close()
+
+
+# ------------------------------------------------------------------------------------------------ chemtrail_burst, spawn
+def chemtrail_cfg(**over):
+    """chemtrail_burst's appcfg defaults (OON.cpp:986-995): unlimited lifetime, mass created, masses of 0.02..0.1 globe radii."""
+    c = capi.EmitterCfg()
+    c.v_factor, c.offset_velo_factor = 0.1, 0.2
+    c.particle_lifetime, c.create_mass = -1.0, 1
+    c.particle_density = 2.0
+    c.velocity_divergence = 1.0
+    c.particle_mass_min = 2.0 * 4.18879 * (0.02 * 5e7) ** 3
+    c.particle_mass_max = 2.0 * 4.18879 * (0.1 * 5e7) ** 3
+    for k, v in over.items():
+        setattr(c, k, v)
+    return c
+
+
+def test_oracle_spawn_and_chemtrail_follow_the_reference():
+    bodies, cfg = synth.make("c4_cloud_100k", n=30)
+    bodies = bodies.copy()
+    bodies["T"][7] = 1234.5
+    bodies["v"][7] = (1e8, -2e8)
+    o = make_oracle(bodies, cfg["props"])
+    o.spawn(7, 4, seed=11)
+    out = o.bodies()
+    assert o.n == 34
+    new = out[30:]
+    assert (new["T"] == np.float32(1234.5)).all() and (new["v"] == bodies["v"][7]).all() and (new["lifetime"] == -1).all()
+    assert (new["density"] == 1000).all()
+    m0 = bodies["mass"][0]
+    assert ((new["mass"] >= m0 / np.float32(9)) & (new["mass"] <= m0 * np.float32(3))).all()
+    assert (np.abs(new["p"] - bodies["p"][0]) <= 0.5 * 1.5e9 * 1.0001).all()      # within 30 globe radii of the PLAYER
+    r = [np.float32(pyoracle.lib().oracle_rand(11, 7 * 2 + j)) for j in range(7)]  # third body: draws 14..20
+    assert new[2]["p"][0] == (r[0] * np.float32(1.5e9)) / np.float32(32767) - np.float32(1.5e9) / np.float32(2) + bodies["p"][0][0]
+    assert new[2]["mass"] == m0 / np.float32(9) + (m0 * np.float32(3) - m0 / np.float32(9)) * r[6] / np.float32(32767)
+    assert new[2]["color"] == (0xffffff & (int(r[4]) * int(r[5])))
+    # chemtrail: positions around emitter.p + emitter.v * offset factor, within 2.5 radii
+    c = chemtrail_cfg()
+    assert o.chemtrail_burst(7, 6, c, seed=12) == 6
+    trail = o.bodies()[34:]
+    centre = bodies["p"][7] + bodies["v"][7] * np.float32(0.2)
+    assert (np.abs(trail["p"] - centre) <= 2.5 * out[7]["r"] * 1.001).all()
+    assert (np.abs(trail["v"] - bodies["v"][7] * np.float32(0.1)) <= 0.5 * 5e7 * 1.001).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("create_mass", [1, 0])
+def test_device_spawn_and_chemtrail_are_bit_identical_to_the_oracle(create_mass):
+    bodies, cfg = synth.make("c4_cloud_100k", n=900)
+    bodies = bodies.copy()
+    bodies["T"][3] = 777.0
+    bodies["v"][3] = (-2e8, 5e7)
+    m3 = float(bodies[3]["mass"])
+    o = make_oracle(bodies, cfg["props"])
+    w = gpu_world(bodies, cfg["props"], capi.MATH_EXACT)
+    c = chemtrail_cfg(create_mass=create_mass, particle_lifetime=0.5, particle_mass_min=m3 * 2e-3, particle_mass_max=m3 * 6e-3)
+    for burst in range(3):
+        o.spawn(3, 40, seed=50 + burst); w.spawn(3, 40, seed=50 + burst)
+        assert o.chemtrail_burst(3, 300, c, seed=70 + burst) == w.chemtrail_burst(3, 300, c, seed=70 + burst)
+        o.step(0.033, 1); w.step(0.033, 1)
+    assert w.entity_count() == o.n
+    got, ref = w.download(), o.bodies()
+    assert bodies_equal_except_color(got, ref)
+    assert (got["color"][900:940] == ref["color"][900:940]).all()      # freshly spawned bodies carry the drawn colour
+    w.close()
