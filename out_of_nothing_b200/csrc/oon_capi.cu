@@ -569,7 +569,7 @@ int ensure_order(oon_world* w, const StepParams& sp, Prof* prof, bool allow_refr
         w->tiles_fresh = false;
         return OON_OK;
     }
-    // allow_refresh == false: between an interact and its integrate the partial sums are indexed by the current
+    // allow_refresh == false: between an interact and its integrate the accumulated sums are indexed by the current
     // slots, so only a missing or invalidated order may be (re)built there, never an aged one.
     const bool stale = w->order_dirty || w->order_kind == 0 ||
                        (allow_refresh && (w->order_kind != kind || (kind == 2 && w->order_age >= w->resort_every)));
