@@ -109,7 +109,8 @@ def test_device_emitter_is_bit_identical_to_the_oracle(n, create_mass):
         kg = w.emit_particles(emitter, n, c, nozzles, seed=1000 + burst)
         assert ko == kg
     assert w.entity_count() == o.n
-    assert bodies_equal_except_color(w.download(), o.bodies())
+    ok, field = bodies_equal_except_color(w.download(), o.bodies())
+    assert ok, field
     if not create_mass and n == 1000:
         assert o.n < 700 + 3000                                   # some particles were refused: the emitter ran dry
     w.close()
@@ -140,7 +141,8 @@ def test_thrusting_player_scene_with_expiring_exhaust(mode):
         assert pair_list(w.debug_fetch_pairs(1)) == pair_list(tr["touches"])
         got, ref = w.download(), o.bodies()
         if mode == capi.MATH_EXACT:
-            assert bodies_equal_except_color(got, ref), frame
+            ok, field = bodies_equal_except_color(got, ref)
+            assert ok, (frame, field)
         else:
             assert (got["T"] == ref["T"]).all() and (got["lifetime"] == ref["lifetime"]).all() and (got["r"] == ref["r"]).all()
     assert o.n > 1010 and w.drain_events()["removed"] > 50        # exhaust was created and swept
@@ -207,6 +209,7 @@ def test_device_spawn_and_chemtrail_are_bit_identical_to_the_oracle(create_mass)
         o.step(0.033, 1); w.step(0.033, 1)
     assert w.entity_count() == o.n
     got, ref = w.download(), o.bodies()
-    assert bodies_equal_except_color(got, ref)
+    ok, field = bodies_equal_except_color(got, ref)
+    assert ok, field
     assert (got["color"][900:940] == ref["color"][900:940]).all()      # freshly spawned bodies carry the drawn colour
     w.close()
