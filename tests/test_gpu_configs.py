@@ -92,3 +92,30 @@ def test_c3_dense_13k_friction_schedule_and_expiry(mode):
     # lifetimes U(1,10) s scaled to U(0.03, 0.3) s: bodies expire from the first frame on (dt = 0.033)
     removed = run_config("c3_dense_13k", mode, frames=4, schedule={0: 0.2, 2: 0.13, 3: 0.03}, lifetime_scale=0.03)
     assert removed > 100
+
+
+# ---------------------------------------------------------------------------------------------- the reference's own start states
+@pytest.mark.parametrize("fixture", ["earth_moon.state", "two_bodies_realg.state", "two_upclose.state", "two_moons.save",
+                                     "dense_black_hole.save", "kat3_start.state", "uncompressed_0.0.1.sav"])
+@pytest.mark.parametrize("n2n", [None, True])
+def test_every_shipped_start_state_runs_bit_identically(fixture, n2n):
+    """The session files the reference ships under test/user/session and test/regression (gravity modes 0/1/2/3, 2…641
+    bodies, model versions 0.0.1…0.1.4), with the `interactions` flag of their header and with --interact: 40 frames in
+    EXACT mode are bit-identical to the oracle; one teacher-forced FAST frame keeps T, lifetimes and the count."""
+    from helpers import load_golden, props_of
+    s = load_golden(fixture)
+    props = props_of(s) if n2n is None else props_of(s, interact_n2n=True)
+    o = make_oracle(s.bodies, props)
+    w = gpu_world(s.bodies, props, capi.MATH_EXACT)
+    for _ in range(4):
+        o.step(0.033, 10); w.step(0.033, 10)
+        assert w.entity_count() == o.n
+        ok, field = bodies_equal_except_color(w.download(), o.bodies())
+        assert ok, (fixture, field)
+    w.math_mode = capi.MATH_FAST
+    o.step(0.033, 1); w.step(0.033, 1)
+    got, ref = w.download(), o.bodies()
+    assert len(got) == len(ref)
+    for f in ("T", "lifetime", "r"):
+        assert (got[f] == ref[f]).all(), (fixture, f)
+    w.close()
