@@ -139,13 +139,21 @@ def run_reference(args):
     value = inter / secs
     sample = "first %d bodies of the %d-body %s world, %d frames after %d warm-up, oracle<float> (-O2 -ffp-contract=off)" % (
         n_sample, cfg_n, args.workload, args.steps, args.warmup)
+    # the reference's CURRENT number type is double (Cfg.hpp:6; every shipped fixture was written by the float build):
+    # a short leg of the double oracle on the same sample, reported beside the float figure
+    od = pyoracle.OracleWorld(double=True)
+    od.set_props(**cfg["props"]); od.set_bodies(bodies)
+    d_steps = 2
+    d_secs = od.time_steps(cfg["dt"], d_steps)
+    value_f64 = d_steps * n_sample * (n_sample - 1) / d_secs
     line = {
         "impl": "reference", "metric": "body_pair_interactions_per_sec", "value": value, "unit": "interactions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
         "steps_per_sec": args.steps / secs, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "n_bodies": cfg_n, "sample_bodies": n_sample, "dt": cfg["dt"], **cfg["props"]},
-        "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": 1, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": 1, "kind": "port", "sample": sample,
+                         "value_double_build": value_f64, "double_build_sample": "%d frames of oracle<double> on the same bodies" % d_steps},
         "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
