@@ -82,6 +82,7 @@ struct oon_world {
     uint32_t cblock = 0;      // bodies per canonical block (block == cblock * 8 / nranks)
     uint32_t n_local = 0;     // host view of the live local count
     bool has_mortals = false; // any body with lifetime > 0 or a non-unlimited non-positive lifetime
+    uint32_t player_ndx = 0;  // player_entity_ndx(): the sweep inside oon_step tests the bodies after it (OON.cpp:1089)
 
     SoAStorage soa[2];        // [cur] is live; the other one is the sweep target
     int cur = 0;
@@ -101,7 +102,8 @@ struct oon_world {
     uint32_t epoch = 0;                                  // packs so far; slice g of buffer epoch&1 is valid once flags[g] >= epoch
     uint32_t waited_epoch = 0;                           // last epoch a kernel of this stream has waited for
     uint32_t* flags = nullptr;                           // [nranks], written by the peers
-    uint32_t* timeouts = nullptr;                        // waits that gave up
+    uint32_t* timeouts = nullptr;                        // waits that gave up (device alias of timeouts_host)
+    uint32_t* timeouts_host = nullptr;                   // mapped pinned word: read after every synchronisation (sync_main)
     void* ipc_stage = nullptr;                           // device staging for the handle exchange
     float* peer_tiles[2][8] = {};                        // peers' exchange buffers (imported), indexed by rank
     uint32_t* peer_flags[8] = {};                        // peers' flag arrays (imported)
@@ -167,6 +169,23 @@ int fail(oon_world* w, int code, const char* fmt, ...) {
 #define NC(w, call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(w, OON_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); } while (0)
 #define CHECK_W(w) do { if (!(w)) return OON_ERR_INVALID; if ((w)->sticky != OON_OK) return (w)->sticky; if (cudaSetDevice((w)->device) != cudaSuccess) return fail(w, OON_ERR_CUDA, "cudaSetDevice(%d) failed", (w)->device); } while (0)
 
+// Wait for the main stream, then look at the peer-to-peer exchange's time-out word (mapped host memory the kernels bump
+// when a wait for a peer's slice gives up): a kernel that carried on without a slice has produced garbage and has broken
+// the epoch protocol, so the failure is sticky — every later call on the handle refuses to run.
+int peers_ok(oon_world* w) {
+    if (w->timeouts_host) {
+        const uint32_t t = *static_cast<volatile uint32_t*>(w->timeouts_host);
+        if (t) return fail(w, OON_ERR_NCCL, "peer-to-peer exchange: %u waits for a peer's slice timed out (a rank fell out of step); the world is no longer valid", t);
+    }
+    return OON_OK;
+}
+int sync_main(oon_world* w) {
+    cudaError_t e = cudaStreamSynchronize(w->stream);
+    if (e != cudaSuccess) return fail(w, OON_ERR_CUDA, "cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+    return peers_ok(w);
+}
+#define SYNC(w) do { int s_ = sync_main(w); if (s_) return s_; } while (0)
+
 template <class T>
 int dev_alloc(oon_world* w, T** p, size_t count) {
     *p = nullptr;
@@ -213,7 +232,7 @@ uint32_t round_up(uint64_t x, uint32_t m) { return uint32_t((x + m - 1) / m * m)
 int barrier(oon_world* w) {
     if (w->nranks == 1 || !w->comm) return OON_OK;
     NC(w, g_nccl.AllGather(static_cast<char*>(w->ipc_stage) + size_t(w->rank) * 4, w->ipc_stage, 4, ncclChar, w->comm, w->stream));
-    CU(w, cudaStreamSynchronize(w->stream));
+    SYNC(w);
     return OON_OK;
 }
 
@@ -250,7 +269,7 @@ int p2p_open(oon_world* w) {
         CU(w, cudaMemcpyAsync(stage + w->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, w->stream));
         NC(w, g_nccl.AllGather(stage + w->rank, stage, sizeof(IpcMsg), ncclChar, w->comm, w->stream));
         CU(w, cudaMemcpyAsync(all.data(), stage, sizeof(IpcMsg) * size_t(w->nranks), cudaMemcpyDeviceToHost, w->stream));
-        CU(w, cudaStreamSynchronize(w->stream));
+        SYNC(w);
         return OON_OK;
     };
     int rc = gather();
@@ -287,7 +306,7 @@ int p2p_open(oon_world* w) {
 // (Re)allocate the exchange buffer(s) for `need_slots` slots.  Collective on sharded worlds (every rank lays the
 // same world out at the same time).
 int realloc_exchange(oon_world* w, size_t need_slots) {
-    CU(w, cudaStreamSynchronize(w->stream));
+    SYNC(w);
     if (w->p2p) {
         p2p_close_tiles(w);
         int rc = barrier(w);                               // every peer has unmapped my buffers before I free them
@@ -326,7 +345,7 @@ int layout(oon_world* w, uint64_t n_total, uint32_t keep) {
         SoAStorage fresh;
         int rc = soa_alloc(w, fresh, cap);
         if (rc) return rc;
-        if (keep) { rc = soa_copy(w, fresh, w->soa[w->cur], keep); if (rc) return rc; CU(w, cudaStreamSynchronize(w->stream)); }
+        if (keep) { rc = soa_copy(w, fresh, w->soa[w->cur], keep); if (rc) return rc; SYNC(w); }
         soa_free(w->soa[w->cur]);
         soa_free(w->soa[w->cur ^ 1]);
         w->soa[w->cur] = fresh;
@@ -510,7 +529,7 @@ int timed(oon_world* w, Prof* prof, int cls, F&& body) {
 
 int prof_collect(oon_world* w, Prof* prof) {
     int rc = OON_OK;
-    if (cudaStreamSynchronize(w->stream) != cudaSuccess) rc = fail(w, OON_ERR_CUDA, "synchronize failed");
+    rc = sync_main(w);
     for (Prof::Span& sp : prof->spans) {
         float ms = 0.f;
         if (rc == OON_OK && cudaEventElapsedTime(&ms, sp.a, sp.b) != cudaSuccess) rc = fail(w, OON_ERR_CUDA, "cudaEventElapsedTime failed");
@@ -763,7 +782,7 @@ int sync_count(oon_world* w) {
     if (w->nranks == 1) {
         uint32_t n = 0;
         CU(w, cudaMemcpyAsync(&n, w->d_n, sizeof n, cudaMemcpyDeviceToHost, w->stream));
-        CU(w, cudaStreamSynchronize(w->stream));
+        SYNC(w);
         w->n_local = n;
         w->n_total = n;
         return OON_OK;
@@ -772,7 +791,7 @@ int sync_count(oon_world* w) {
     CU(w, cudaMemcpyAsync(w->d_counts + w->rank, w->d_n, sizeof(uint32_t), cudaMemcpyDeviceToDevice, w->stream));
     NC(w, g_nccl.AllGather(w->d_counts + w->rank, w->d_counts, 1, ncclUint32, w->comm, w->stream));
     CU(w, cudaMemcpyAsync(w->counts.data(), w->d_counts, sizeof(uint32_t) * size_t(w->nranks), cudaMemcpyDeviceToHost, w->stream));
-    CU(w, cudaStreamSynchronize(w->stream));
+    SYNC(w);
     w->n_local = w->counts[size_t(w->rank)];
     uint64_t total = 0;
     for (uint32_t c : w->counts) total += c;
@@ -803,7 +822,7 @@ int step_impl(oon_world* w, float dt, uint32_t nsteps, Prof* prof) {
         const bool resort_due = wants_morton(w, sp) && (w->order_age >= w->resort_every || w->next_order_pending);
         const bool fuse = !sweep && !last && !resort_due;
         if ((rc = do_integrate(w, sp, true, true, fuse, prof))) return rc;
-        if (sweep && (rc = do_sweep(w, 0, prof))) return rc;
+        if (sweep && (rc = do_sweep(w, w->player_ndx, prof))) return rc;
         if (!fuse && !last && (rc = do_intrinsic_pack(w, sp, true, prof))) return rc;
     }
     w->steps += nsteps;
@@ -925,7 +944,9 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
     }
     if (nranks > 1) {
         CUB_(cudaMalloc(&w->flags, sizeof(uint32_t) * size_t(nranks))); CUB_(cudaMemset(w->flags, 0, sizeof(uint32_t) * size_t(nranks)));
-        CUB_(cudaMalloc(&w->timeouts, sizeof(uint32_t))); CUB_(cudaMemset(w->timeouts, 0, sizeof(uint32_t)));
+        CUB_(cudaHostAlloc(reinterpret_cast<void**>(&w->timeouts_host), sizeof(uint32_t), cudaHostAllocMapped));
+        *w->timeouts_host = 0u;
+        CUB_(cudaHostGetDevicePointer(reinterpret_cast<void**>(&w->timeouts), w->timeouts_host, 0));
         CUB_(cudaMalloc(&w->ipc_stage, 256 * size_t(nranks)));
         CUB_(cudaMalloc(&w->runinfo, sizeof(int) * 4 * size_t(nranks))); CUB_(cudaMemset(w->runinfo, 0, sizeof(int) * 4 * size_t(nranks)));
         CUB_(cudaMalloc(&w->d_counts, sizeof(uint32_t) * size_t(nranks)));
@@ -967,7 +988,7 @@ int oon_destroy(oon_world* w) {
     if (w->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(w->comm);
     soa_free(w->soa[0]); soa_free(w->soa[1]);
     cudaFree(w->tiles_buf[0]); cudaFree(w->tiles_buf[1]); cudaFree(w->acc); cudaFree(w->touch); cudaFree(w->fx_scale); cudaFree(w->rank_stats);
-    cudaFree(w->flags); cudaFree(w->timeouts); cudaFree(w->ipc_stage); cudaFree(w->runinfo); cudaFree(w->d_counts); cudaFree(w->partial); cudaFree(w->scratch4); cudaFree(w->kick); cudaFree(w->d_n); cudaFree(w->d_removed_count);
+    cudaFree(w->flags); if (w->timeouts_host) cudaFreeHost(w->timeouts_host); cudaFree(w->ipc_stage); cudaFree(w->runinfo); cudaFree(w->d_counts); cudaFree(w->partial); cudaFree(w->scratch4); cudaFree(w->kick); cudaFree(w->d_n); cudaFree(w->d_removed_count);
     cudaFree(w->counters); cudaFree(w->sweep_temp); cudaFree(w->sweep_scratch); cudaFree(w->removed_idx); cudaFree(w->aos_dev);
     cudaFree(w->xyr_dev); cudaFree(w->cap.coll); cudaFree(w->cap.touch);
     cudaFree(w->inv); cudaFree(w->order_temp); cudaFree(w->order_keys); cudaFree(w->order_vals); cudaFree(w->order_bounds);
@@ -1007,36 +1028,75 @@ int oon_get_math_mode(const oon_world* w, int* mode) {
     return OON_OK;
 }
 
-int oon_upload(oon_world* w, const oon_body_f32* bodies, uint64_t n) {
-    CHECK_W(w);
+// Replace the world by n bodies.  `src` = the whole table in host order (is_block == false) or this rank's block of it
+// (is_block == true, `count` bodies starting at global index rank * block).  Only the rank's own block crosses the bus.
+// Whether any body can expire (then the frames include the sweep) is found by the unpack kernel, one flag per rank; a
+// sharded world agrees on it with a one-word all-gather — round 1 walked the whole 60-byte-per-body host table on every
+// rank for this, which cost more than the PCIe copy of the block.
+static int upload_common(oon_world* w, const oon_body_f32* src, bool is_block, uint64_t count, uint64_t n) {
     { int qrc = quiesce_aux(w); if (qrc) return qrc; }
-    if (n && !bodies) return fail(w, OON_ERR_INVALID, "null body table");
-    // Does any body have a finite lifetime (then the frames include the sweep and keep the identity order)?  A sharded
-    // world must know before it accepts the table (every rank sees the whole table); a single-GPU world lets the unpack
-    // kernel find out — walking 60-byte records on the host cost more than the PCIe copy of the same table.
-    bool mortals = false;
-    if (w->nranks > 1)
-        for (uint64_t i = 0; i < n; ++i) mortals |= mortal(bodies[i].lifetime);
+    if (n && !src && !(is_block && !count)) return fail(w, OON_ERR_INVALID, "null body table");
     int rc = layout(w, n, 0);
     if (rc) return rc;
     const uint64_t lo = uint64_t(w->rank) * w->block;
+    if (is_block && count != w->n_local)
+        return fail(w, OON_ERR_INVALID, "upload_local: rank %d of %d owns %u bodies of a %llu-body world (from index %llu), got %llu",
+                    w->rank, w->nranks, w->n_local, (unsigned long long)n, (unsigned long long)lo, (unsigned long long)count);
+    const oon_body_f32* mine = is_block ? src : src + lo;
     CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));     // doubles as the unpack kernel's "mortal seen" flag
     if (w->n_local) {
         if ((rc = ensure_aos(w, w->n_local))) return rc;
-        CU(w, cudaMemcpyAsync(w->aos_dev, bodies + lo, size_t(w->n_local) * sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
+        CU(w, cudaMemcpyAsync(w->aos_dev, mine, size_t(w->n_local) * sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
         w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, 0, w->n_local, w->d_removed_count);
         CU(w, cudaGetLastError());
     }
     CU(w, cudaMemcpyAsync(w->d_n, &w->n_local, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
-    uint32_t seen = 0;
-    CU(w, cudaMemcpyAsync(&seen, w->d_removed_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    std::vector<uint32_t> seen(size_t(w->nranks), 0u);
+    if (w->nranks > 1) {
+        CU(w, cudaMemcpyAsync(w->d_counts + w->rank, w->d_removed_count, sizeof(uint32_t), cudaMemcpyDeviceToDevice, w->stream));
+        NC(w, g_nccl.AllGather(w->d_counts + w->rank, w->d_counts, 1, ncclUint32, w->comm, w->stream));
+        CU(w, cudaMemcpyAsync(seen.data(), w->d_counts, sizeof(uint32_t) * seen.size(), cudaMemcpyDeviceToHost, w->stream));
+    } else {
+        CU(w, cudaMemcpyAsync(seen.data(), w->d_removed_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    }
     CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));
-    CU(w, cudaStreamSynchronize(w->stream));     // the caller may reuse `bodies` immediately (pageable memory)
-    w->has_mortals = mortals || seen != 0;
+    SYNC(w);                                         // the caller may reuse the host table immediately (pageable memory)
+    uint32_t any = 0;
+    for (uint32_t v : seen) any |= v;
+    w->has_mortals = any != 0;
     for (int g = 0; g < w->nranks && !w->counts.empty(); ++g) {          // the even split, until a sweep makes the blocks ragged
         const uint64_t glo = uint64_t(g) * w->block;
         w->counts[size_t(g)] = n > glo ? uint32_t(std::min<uint64_t>(w->block, n - glo)) : 0u;
     }
+    return OON_OK;
+}
+
+int oon_upload(oon_world* w, const oon_body_f32* bodies, uint64_t n) {
+    CHECK_W(w);
+    return upload_common(w, bodies, false, 0, n);
+}
+
+int oon_upload_local(oon_world* w, const oon_body_f32* block, uint64_t count, uint64_t n_total) {
+    CHECK_W(w);
+    return upload_common(w, block, true, count, n_total);
+}
+
+int oon_shard_range(uint64_t n_total, int rank, int nranks, uint64_t* first_out, uint64_t* count_out) {
+    if (nranks < 1 || rank < 0 || rank >= nranks) return OON_ERR_INVALID;
+    const bool canon = (nranks == 1 || nranks == 2 || nranks == 4 || nranks == 8);      // == layout()
+    const uint32_t nblocks = canon ? 8u : uint32_t(nranks);
+    const uint64_t cblock = std::max<uint64_t>(TS, (((n_total + nblocks - 1) / nblocks) + TS - 1) / TS * TS);
+    const uint64_t block = cblock * (nblocks / uint32_t(nranks));
+    const uint64_t lo = std::min<uint64_t>(n_total, uint64_t(rank) * block);
+    if (first_out) *first_out = lo;
+    if (count_out) *count_out = std::min<uint64_t>(block, n_total - lo);
+    return OON_OK;
+}
+
+int oon_set_player_index(oon_world* w, uint64_t ndx) {
+    CHECK_W(w);
+    if (ndx > 0x3fffffffull) return fail(w, OON_ERR_INVALID, "player index %llu out of range", (unsigned long long)ndx);
+    w->player_ndx = uint32_t(ndx);
     return OON_OK;
 }
 
@@ -1091,7 +1151,30 @@ int oon_download(oon_world* w, oon_body_f32* out, uint64_t capacity, uint64_t* n
         if (c) CU(w, cudaMemcpyAsync(out + at, w->aos_dev + size_t(g) * w->block, size_t(c) * sizeof(oon_body_f32), cudaMemcpyDeviceToHost, w->stream));
         at += c;
     }
-    CU(w, cudaStreamSynchronize(w->stream));
+    SYNC(w);
+    return OON_OK;
+}
+
+// Shard-local read-back: the bodies this rank owns, nothing else — no collective on the data path, one D2H copy of the
+// rank's own block (a full oon_download on 8 ranks all-gathers 60 B/body and then copies the whole table on EVERY rank).
+int oon_download_local(oon_world* w, oon_body_f32* block_out, uint64_t capacity, uint64_t* first_out, uint64_t* n_out) {
+    CHECK_W(w);
+    int rc = sync_count(w);                                  // only worlds whose bodies can expire pay for the count exchange
+    if (rc) return rc;
+    uint64_t first = 0;
+    for (int g = 0; g < w->rank; ++g) first += rank_count(w, g);
+    const uint64_t n = w->nranks == 1 ? w->n_total : w->n_local;
+    if (first_out) *first_out = first;
+    if (n_out) *n_out = n;
+    if (n > capacity) return fail(w, OON_ERR_CAPACITY, "local download needs room for %llu bodies, got %llu", (unsigned long long)n, (unsigned long long)capacity);
+    if (n && !block_out) return fail(w, OON_ERR_INVALID, "null output");
+    if (n) {
+        if ((rc = ensure_aos(w, n))) return rc;
+        w->launches += launch_pack_f32(w->stream, w->soa[w->cur].d, w->aos_dev, 0, uint32_t(n));
+        CU(w, cudaGetLastError());
+        CU(w, cudaMemcpyAsync(block_out, w->aos_dev, size_t(n) * sizeof(oon_body_f32), cudaMemcpyDeviceToHost, w->stream));
+    }
+    SYNC(w);
     return OON_OK;
 }
 
@@ -1160,7 +1243,7 @@ int oon_download_render(oon_world* w, float* xyr, uint64_t capacity, uint64_t* n
     if (rc) return rc;
     CU(w, cudaEventSynchronize(w->ev_render_done));
     w->render_pending = false;
-    return OON_OK;
+    return peers_ok(w);
 }
 
 int oon_download_render_begin(oon_world* w, float* xyr_pinned, uint64_t capacity) {
@@ -1174,7 +1257,7 @@ int oon_download_render_end(oon_world* w, uint64_t* n_out) {
     CU(w, cudaEventSynchronize(w->ev_render_done));
     w->render_pending = false;
     if (n_out) *n_out = w->render_count;
-    return OON_OK;
+    return peers_ok(w);
 }
 
 int oon_body_count(oon_world* w, uint64_t* n_out) {
@@ -1202,7 +1285,7 @@ int oon_add_bodies(oon_world* w, const oon_body_f32* bodies, uint64_t k) {
     w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, old_n, uint32_t(k), nullptr);
     CU(w, cudaGetLastError());
     CU(w, cudaMemcpyAsync(w->d_n, &w->n_local, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
-    CU(w, cudaStreamSynchronize(w->stream));
+    SYNC(w);
     return OON_OK;
 }
 
@@ -1247,7 +1330,7 @@ static int emit_common(oon_world* w, int kind, uint64_t base_ndx, uint64_t paren
     uint32_t emitted = 0;
     CU(w, cudaMemcpyAsync(&emitted, w->d_removed_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
     CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));
-    CU(w, cudaStreamSynchronize(w->stream));
+    SYNC(w);
     if ((rc = layout(w, uint64_t(old_n) + emitted, old_n + emitted))) return rc;   // bookkeeping only: capacity is there
     if (emitted && kind != EMIT_SPAWN) w->has_mortals |= mortal(cfg->particle_lifetime);
     if (emitted_out) *emitted_out = emitted;
@@ -1283,7 +1366,7 @@ int oon_get_body(oon_world* w, uint64_t ndx, oon_body_f32* out) {
     w->launches += launch_pack_f32(w->stream, w->soa[w->cur].d, w->aos_dev, uint32_t(ndx), 1);
     CU(w, cudaGetLastError());
     CU(w, cudaMemcpyAsync(out, w->aos_dev, sizeof(oon_body_f32), cudaMemcpyDeviceToHost, w->stream));
-    CU(w, cudaStreamSynchronize(w->stream));
+    SYNC(w);
     return OON_OK;
 }
 
@@ -1300,7 +1383,7 @@ int oon_set_body(oon_world* w, uint64_t ndx, const oon_body_f32* in) {
     CU(w, cudaMemcpyAsync(w->aos_dev, in, sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
     w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, uint32_t(ndx), 1, nullptr);
     CU(w, cudaGetLastError());
-    CU(w, cudaStreamSynchronize(w->stream));
+    SYNC(w);
     w->tiles_fresh = false;
     return OON_OK;
 }
@@ -1325,7 +1408,7 @@ int oon_remove_body(oon_world* w, uint64_t ndx) {
     }
     w->n_local = n - 1; w->n_total = n - 1;
     CU(w, cudaMemcpyAsync(w->d_n, &w->n_local, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
-    CU(w, cudaStreamSynchronize(w->stream));
+    SYNC(w);
     w->tiles_fresh = false;
     w->order_dirty = true;
     return OON_OK;
@@ -1376,20 +1459,10 @@ int oon_sweep_expired(oon_world* w, uint64_t player_ndx) {
     return do_sweep(w, uint32_t(player_ndx), nullptr);
 }
 
-// Peer-to-peer exchange: a kernel that gave up waiting for a peer's slice has produced garbage; make that a sticky error.
-static int check_peers_arrived(oon_world* w) {
-    if (!w->p2p) return OON_OK;
-    uint32_t t = 0;
-    CU(w, cudaMemcpyAsync(&t, w->timeouts, sizeof t, cudaMemcpyDeviceToHost, w->stream));
-    CU(w, cudaStreamSynchronize(w->stream));
-    if (t) return fail(w, OON_ERR_NCCL, "peer-to-peer exchange: %u waits for a peer's slice timed out (a rank fell out of step)", t);
-    return OON_OK;
-}
-
 int oon_synchronize(oon_world* w) {
     CHECK_W(w);
-    CU(w, cudaStreamSynchronize(w->stream));
-    return check_peers_arrived(w);
+    SYNC(w);
+    return OON_OK;
 }
 
 int oon_exchange_kind(const oon_world* w, int* kind) {
@@ -1404,8 +1477,7 @@ int oon_drain_events(oon_world* w, oon_events* out) {
     unsigned long long c[C_COUNT];
     CU(w, cudaMemcpyAsync(c, w->counters, sizeof c, cudaMemcpyDeviceToHost, w->stream));
     CU(w, cudaMemsetAsync(w->counters, 0, sizeof(unsigned long long) * C_CAPTURE_COLL, w->stream));   // capture cursors live on
-    CU(w, cudaStreamSynchronize(w->stream));
-    { int prc = check_peers_arrived(w); if (prc) return prc; }
+    SYNC(w);
     out->steps = w->steps; w->steps = 0;
     out->collisions = c[C_COLLISIONS]; out->touches = c[C_TOUCHES]; out->player_touches = c[C_PLAYER_TOUCHES];
     out->terminated = c[C_TERMINATED]; out->removed = c[C_REMOVED];
@@ -1424,7 +1496,7 @@ int oon_timer_stop(oon_world* w, float* elapsed_ms) {
     CU(w, cudaEventRecord(w->ev_stop, w->stream));
     CU(w, cudaEventSynchronize(w->ev_stop));
     CU(w, cudaEventElapsedTime(elapsed_ms, w->ev_start, w->ev_stop));
-    return OON_OK;
+    return peers_ok(w);
 }
 
 static int bench_frames_impl(oon_world* w, float dt, uint32_t nsteps, uint64_t flush_bytes, double* ms_sum, Prof* prof) {
@@ -1450,7 +1522,7 @@ static int bench_frames_impl(oon_world* w, float dt, uint32_t nsteps, uint64_t f
         rc = step_impl(w, dt, 1, prof);
         if (rc == OON_OK && cudaEventRecord(ev[2 * k + 1], w->stream) != cudaSuccess) rc = fail(w, OON_ERR_CUDA, "cudaEventRecord failed");
     }
-    if (rc == OON_OK && cudaStreamSynchronize(w->stream) != cudaSuccess) rc = fail(w, OON_ERR_CUDA, "synchronize failed");
+    if (rc == OON_OK) rc = sync_main(w);
     if (prof) { const int crc = prof_collect(w, prof); if (rc == OON_OK) rc = crc; }
     if (rc == OON_OK) {
         for (uint32_t k = 0; k < nsteps; ++k) {
@@ -1501,7 +1573,7 @@ int oon_measure_copy_bandwidth(int device, double* gbs_out) {
 
 int oon_debug_capture_pairs(oon_world* w, uint64_t capacity) {
     CHECK_W(w);
-    CU(w, cudaStreamSynchronize(w->stream));
+    SYNC(w);
     cudaFree(w->cap.coll); cudaFree(w->cap.touch);
     w->cap = CaptureBuf{};
     if (capacity) {
@@ -1523,7 +1595,7 @@ int oon_debug_fetch_pairs(oon_world* w, int which, uint32_t* pairs, uint64_t cap
     unsigned long long cnt = 0;
     const int ci = which == 0 ? C_CAPTURE_COLL : C_CAPTURE_TOUCH;
     CU(w, cudaMemcpyAsync(&cnt, w->counters + ci, sizeof cnt, cudaMemcpyDeviceToHost, w->stream));
-    CU(w, cudaStreamSynchronize(w->stream));
+    SYNC(w);
     if (n_out) *n_out = cnt;
     if (cnt > w->cap.capacity) return fail(w, OON_ERR_CAPACITY, "pair capture overflowed: %llu pairs, capacity %u", cnt, w->cap.capacity);
     if (cnt > capacity) return fail(w, OON_ERR_CAPACITY, "output too small for %llu pairs", cnt);
@@ -1532,7 +1604,7 @@ int oon_debug_fetch_pairs(oon_world* w, int which, uint32_t* pairs, uint64_t cap
         CU(w, cudaMemcpyAsync(pairs, which == 0 ? w->cap.coll : w->cap.touch, size_t(cnt) * sizeof(uint2), cudaMemcpyDeviceToHost, w->stream));
     }
     CU(w, cudaMemsetAsync(w->counters + ci, 0, sizeof(unsigned long long), w->stream));
-    CU(w, cudaStreamSynchronize(w->stream));
+    SYNC(w);
     return OON_OK;
 }
 
@@ -1544,7 +1616,7 @@ int oon_debug_fetch_kick(oon_world* w, float* dv, uint64_t capacity, uint64_t* n
     if (n_out) *n_out = n;
     if (n > capacity) return fail(w, OON_ERR_CAPACITY, "output too small for %llu bodies", (unsigned long long)n);
     if (n) CU(w, cudaMemcpyAsync(dv, w->kick, size_t(n) * sizeof(float2), cudaMemcpyDeviceToHost, w->stream));
-    CU(w, cudaStreamSynchronize(w->stream));
+    SYNC(w);
     return OON_OK;
 }
 
@@ -1552,13 +1624,13 @@ int oon_debug_fetch_removed(oon_world* w, uint32_t* idx, uint64_t capacity, uint
     CHECK_W(w);
     uint32_t cnt = 0;
     CU(w, cudaMemcpyAsync(&cnt, w->d_removed_count, sizeof cnt, cudaMemcpyDeviceToHost, w->stream));
-    CU(w, cudaStreamSynchronize(w->stream));
+    SYNC(w);
     if (n_out) *n_out = cnt;
     if (cnt > capacity) return fail(w, OON_ERR_CAPACITY, "output too small for %u indices", cnt);
     if (cnt) {
         if (!idx) return fail(w, OON_ERR_INVALID, "null output");
         CU(w, cudaMemcpyAsync(idx, w->removed_idx, size_t(cnt) * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
-        CU(w, cudaStreamSynchronize(w->stream));
+        SYNC(w);
     }
     return OON_OK;
 }

@@ -31,6 +31,7 @@ constexpr int CTA_THREADS = 256;
 constexpr int K1_TARGETS_PER_CTA = OON_K1_THREADS * OON_K1_T;   // target slots per CTA of the FAST interact kernel
 constexpr float BOX_EMPTY = 3.0e38f;       // |coordinate| of an empty box (finite on purpose)
 constexpr uint32_t ID_NONE = 0xffffffffu;
+constexpr uint32_t ID_PLAYER_BIT = 0x80000000u;   // id word of a tile slot: global body index (< 2^30) | this bit for a body with thrusters
 
 // A dead slot (padding, or a body with lifetime == 0) is parked far away with no mass and a
 // negative radius: it attracts nothing, never collides and never comes near anything.

@@ -17,6 +17,15 @@ from . import capi
 from .capi import BODY_F32, EmitterCfg, Events, OonError, Props
 
 
+def recalc_radii(bodies: np.ndarray) -> np.ndarray:
+    """``Entity::recalc()`` (Entity.cpp:14-20) for a whole table: r = radius_from_mass_and_density(mass, density).
+    (The colour half of recalc() cannot be restated: Phys::T_to_RGB_and_BV is absent from the reference tree.)"""
+    from .synth import radius_from_mass_and_density
+    out = np.ascontiguousarray(bodies).copy()
+    out["r"] = radius_from_mass_and_density(out["mass"], out["density"])
+    return out
+
+
 class Properties:
     """Live view of ``World::props`` (World.hpp:59-69): attribute writes go straight to the device handle."""
 
@@ -126,6 +135,41 @@ class World:
         self._check(self._L.oon_download(self._h, ptr, capacity, ctypes.byref(got)))
         return got.value
 
+    # shard-local I/O (sharded worlds): only this rank's block crosses the bus, no collective on the data path
+    def local_range(self, n_total: int):
+        """(first, count) of the block this rank owns in a freshly uploaded world of n_total bodies."""
+        first, count = ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self._L.oon_shard_range(n_total, self.rank, self.nranks, ctypes.byref(first), ctypes.byref(count)))
+        return first.value, count.value
+
+    def upload_local(self, block: np.ndarray, n_total: int):
+        block = np.ascontiguousarray(block)
+        assert block.dtype.itemsize == 60
+        self._check(self._L.oon_upload_local(self._h, block.ctypes.data if block.shape[0] else None, block.shape[0], n_total))
+
+    def upload_local_ptr(self, ptr: int, count: int, n_total: int):
+        self._check(self._L.oon_upload_local(self._h, ptr, count, n_total))
+
+    def download_local(self):
+        """-> (first global index, this rank's bodies)."""
+        cap = max(1, self.local_range(max(1, self.entity_count()))[1])
+        out = np.zeros(cap, BODY_F32)
+        first, got = ctypes.c_uint64(), ctypes.c_uint64()
+        rc = self._L.oon_download_local(self._h, out.ctypes.data, cap, ctypes.byref(first), ctypes.byref(got))
+        if rc == capi.ERR_CAPACITY:                          # ragged blocks after sweeps: a rank may hold more than the even share
+            out = np.zeros(got.value, BODY_F32)
+            rc = self._L.oon_download_local(self._h, out.ctypes.data, got.value, ctypes.byref(first), ctypes.byref(got))
+        self._check(rc)
+        return first.value, out[: got.value]
+
+    def download_local_ptr(self, ptr: int, capacity: int):
+        first, got = ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self._L.oon_download_local(self._h, ptr, capacity, ctypes.byref(first), ctypes.byref(got)))
+        return first.value, got.value
+
+    def set_player_index(self, ndx: int):
+        self._check(self._L.oon_set_player_index(self._h, ndx))
+
     def download_render(self) -> np.ndarray:
         n = self.entity_count()
         out = np.zeros((n, 3), np.float32)
@@ -148,17 +192,31 @@ class World:
         self._check(self._L.oon_body_count(self._h, ctypes.byref(n)))
         return n.value
 
-    def add_body(self, body) -> int:
-        """World::add_body (World.cpp:55-70).  Returns the new body's index."""
+    def add_body(self, body, recalc: bool = True) -> int:
+        """World::add_body (World.cpp:55-70): append + ``recalc()`` — the radius is recomputed from mass and density
+        (Entity.cpp:17) like the reference does for every body it adds or loads; ``recalc=False`` keeps the stored
+        radius (raw table edits).  Returns the new body's index."""
         rec = np.zeros(1, BODY_F32)
         rec[0] = body
         n = self.entity_count()
-        self._check(self._L.oon_add_bodies(self._h, rec.ctypes.data, 1))
+        self.add_bodies(rec, recalc=recalc)
         return n
 
-    def add_bodies(self, bodies: np.ndarray):
-        bodies = np.ascontiguousarray(bodies)
+    def add_bodies(self, bodies: np.ndarray, recalc: bool = True):
+        bodies = recalc_radii(bodies) if recalc else np.ascontiguousarray(bodies)
         self._check(self._L.oon_add_bodies(self._h, bodies.ctypes.data, bodies.shape[0]))
+
+    def load(self, snap, recalc: bool = True):
+        """World::load (World_SaveLoad.cpp:125-165): take the knobs of a snapshot header and add its bodies one by one
+        through add_body(), i.e. WITH ``recalc()`` — v0.0.1 snapshots store radii of an older convention and the
+        reference replaces them on load.  ``snap`` = a ``snapshot.Snapshot`` or a path."""
+        from . import snapshot as _snapshot
+        if not hasattr(snap, "bodies"):
+            snap = _snapshot.load(snap)
+        self.set_props(friction=snap.friction, gravity_mode=snap.gravity_mode, gravity=snap.gravity, interact_n2n=snap.interact_n2n)
+        bodies = snap.as_f32()                     # a double-build file is narrowed like oon_upload_f64 does
+        self.upload(recalc_radii(bodies) if recalc else bodies)
+        return snap
 
     def remove_body(self, ndx: int):
         """World::remove_body (World.cpp:72-78): erase, later indices shift down."""

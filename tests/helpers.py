@@ -31,10 +31,11 @@ def props_of(snap, **over):
     return p
 
 
-def make_oracle(bodies, props, double=False, trace=False):
+def make_oracle(bodies, props, double=False, trace=False, recalc=False):
+    """recalc=True: the bodies go through add_body()'s recalc() like World::load does (World_SaveLoad.cpp:156)."""
     o = pyoracle.OracleWorld(double=double)
     o.set_props(**props)
-    o.set_bodies(bodies)
+    o.set_bodies(bodies, recalc=recalc)
     if trace:
         o.trace(True)
     return o

@@ -243,11 +243,12 @@ def test_expiry_and_sweep_sequence_matches(mode):
 
 @pytest.mark.parametrize("fixture,frames", [("realg_test.state", 300), ("multi_cluster_640.save", 60)])
 def test_fixture_worlds_with_finite_lifetimes_exact(fixture, frames):
+    from out_of_nothing_b200.world import recalc_radii
     s = load_golden(fixture)
     assert (s.bodies["lifetime"] > 0).sum() > 0
     props = props_of(s, interact_n2n=True)
-    o = make_oracle(s.bodies, props)
-    w = gpu_world(s.bodies, props, EXACT, capture=0)
+    o = make_oracle(s.bodies, props, recalc=True)            # World::load -> add_body -> recalc(), World_SaveLoad.cpp:156
+    w = gpu_world(recalc_radii(s.bodies), props, EXACT, capture=0)
     done = 0
     while done < frames:
         w.step(DT, 20); o.step(DT, 20); done += 20
@@ -325,16 +326,18 @@ def test_decision_boundaries_dense_sweep():
 
 
 def test_snapshot_14k_world_one_frame():
+    from out_of_nothing_b200.world import recalc_radii
     s = load_golden("snapshot_4_14k.save")
     props = props_of(s, interact_n2n=True)
-    o = make_oracle(s.bodies, props, trace=True)
+    o = make_oracle(s.bodies, props, trace=True, recalc=True)    # loaded like the reference loads it: radii recalculated
     o.step(DT, 1)
     ref, tr = o.bodies(), o.trace_fetch()
-    w = gpu_world(s.bodies, props, EXACT); w.step(DT, 1)
+    loaded = recalc_radii(s.bodies)
+    w = gpu_world(loaded, props, EXACT); w.step(DT, 1)
     ok, field = bodies_equal_except_color(w.download(), ref)
     assert ok, field
     w.close()
-    w = gpu_world(s.bodies, props, FAST); w.step(DT, 1)
+    w = gpu_world(loaded, props, FAST); w.step(DT, 1)
     got = w.download()
     assert pair_list(w.debug_fetch_pairs(0)) == pair_list(tr["collisions"])
     assert pair_list(w.debug_fetch_pairs(1)) == pair_list(tr["touches"])
