@@ -5,8 +5,9 @@
 
 N > 1 is launched by the driver as
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
-one rank per GPU: targets are sharded in contiguous index blocks, sources are all-gathered once per frame by the
-library's own NCCL communicator; torch.distributed only carries the NCCL id, the barriers and the max-over-ranks.
+one rank per GPU: targets are sharded in contiguous index blocks, the source tiles are exchanged once per frame (peer
+stores over NVLink fused into the pack kernel, NCCL all-gather as fallback); torch.distributed only carries the NCCL id,
+the barriers and the max-over-ranks.
 
 Workload (default C4 of BASELINE.json, the configuration the metric and the roofline target are quoted on):
 100 000-body random cloud, gravity only (friction 0), all-pairs, hyperbolic law, dt 0.033, total size fixed as the
@@ -14,9 +15,17 @@ GPU count grows ("strong" scaling).  Rank 0 prints ONE JSON line.
 
 A "step" = one frame: update_intrinsic + update_pairwise + update_global (+ the expired-body sweep when bodies can
 expire).  `value` = steps * N*(N-1) / device time of the K timed frames, inputs resident in HBM.  `e2e` = the same
-metric through the C ABI with host buffers: every frame uploads the body table from pinned host memory, steps once
-and downloads it again.  `--impl reference` times the oracle port of the reference's CPU path (the reference itself
-cannot be built: engine sources absent) on one host core — the reference is single-threaded by construction.
+metric through the C ABI with HOST buffers: every frame uploads the body table from pinned host memory, steps once and
+reads it back (per-rank blocks with oon_upload_local / oon_download_local on sharded worlds).  `--impl reference` times
+the oracle port of the reference's CPU path (the reference itself cannot be built: engine sources absent) on one host
+core — the reference is single-threaded by construction.
+
+Beside the headline line (all outside the timed region):
+  parity_check  N > 1: KAT-1 x 20 frames in EXACT and in FAST mode, and 3 FAST frames of the 100k-body cloud, on the
+                sharded world and on a private 1-GPU world on rank 0's device, compared byte for byte
+  c5            N = 8: BASELINE config C5 (1 M bodies, void sphere) on the 8 GPUs + a short 1-GPU leg on rank 0's device
+                -> the 8-GPU efficiency of the config the 85 % target is quoted on
+  configs       N = 1: C1 (KAT-1), C2, C3 (+ the same world without mortal bodies) in FAST and EXACT mode, C4 in EXACT mode
 """
 from __future__ import annotations
 
@@ -34,6 +43,8 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_INTERACTION = 18          # literal op count of World.cpp:271-288,304,363-364
 INTEGRATE_BYTES_PER_BODY = 77      # BASELINE.md §2 / SURVEY.md §8d
+SETTLE_FRAMES = 150                # frames a freshly uploaded world is advanced before the warm-up (see "settle" in the line)
+FLUSH_BYTES = 256 << 20            # > 126 MB L2, written on the library's stream before every timed frame
 
 
 def parse_args():
@@ -49,6 +60,8 @@ def parse_args():
     ap.add_argument("--cpu-sample-bodies", type=int, default=0)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--settle", type=int, default=-1, help="frames advanced before the warm-up (default %d for worlds >= 32768 bodies, else 0)" % SETTLE_FRAMES)
+    ap.add_argument("--skip-extras", action="store_true", help="headline line only: no parity_check / c5 / configs sub-records")
     return ap.parse_args()
 
 
@@ -137,8 +150,9 @@ def run_reference(args):
     secs = o.time_steps(cfg["dt"], args.steps)
     inter = args.steps * n0 * (n0 - 1)
     value = inter / secs
-    sample = "first %d bodies of the %d-body %s world, %d frames after %d warm-up, oracle<float> (-O2 -ffp-contract=off)" % (
-        n_sample, cfg_n, args.workload, args.steps, args.warmup)
+    sample = ("first %d bodies of the %d-body %s world (a full CPU frame of the whole world would take ~%.0f s), %d frames after %d warm-up, "
+              "oracle<float> (-O2 -ffp-contract=off): a per-interaction rate on a smaller N, not the same world") % (
+        n_sample, cfg_n, args.workload, cfg_n * (cfg_n - 1) / rate, args.steps, args.warmup)
     # the reference's CURRENT number type is double (Cfg.hpp:6; every shipped fixture was written by the float build):
     # a short leg of the double oracle on the same sample, reported beside the float figure
     od = pyoracle.OracleWorld(double=True)
@@ -161,84 +175,232 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+class Ranks:
+    """torch.distributed plumbing of the bench: rendezvous, NCCL ids for the library's own communicators, barriers."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.size = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU baseline)")
+        torch.cuda.set_device(self.local_rank)
+        if self.size > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+
+    def new_world(self, sharded=True):
+        """A world handle: one shard of a world over all ranks (its own NCCL communicator), or a private 1-GPU world."""
+        from out_of_nothing_b200 import capi
+        from out_of_nothing_b200.world import World
+        if self.size == 1 or not sharded:
+            return World(self.local_rank)
+        idt = self.torch.zeros(capi.NCCL_ID_BYTES, dtype=self.torch.uint8, device="cuda")
+        if self.rank == 0:
+            idt.copy_(self.torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=self.torch.uint8))
+        self.dist.broadcast(idt, 0)
+        return World(self.local_rank, self.rank, self.size, bytes(idt.cpu().numpy().tobytes()))
+
+    def barrier(self):
+        if self.size > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, x: float) -> float:
+        if self.size == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(self, ok: bool) -> bool:
+        if self.size == 1:
+            return bool(ok)
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
+
+def load_workload(name, n=None):
+    """-> (bodies, cfg).  c1_kat1 = the reference's own tc-smoke start state (tests/golden), the rest is synthetic."""
+    from out_of_nothing_b200 import snapshot, synth
+    if name == "c1_kat1":
+        s = snapshot.load(os.path.join(ROOT, "tests", "golden", "kat1_start.state"))
+        props = dict(friction=0.01, gravity_mode=s.gravity_mode, gravity=s.gravity, interact_n2n=1, collision_mode=1,
+                     repulsion_stiffness=0.0, loop_mode=0)          # test/regression/tc-smoke.cmd:30-43
+        return s.bodies, dict(props=props, dt=0.033, n=s.n, name=name)
+    return synth.make(name, n=n or None)
+
+
+def timed_frames(w, dt, steps, flush_bytes):
+    """Device time (ms) of `steps` frames: one event pair per frame with the L2 flushed before each, or one pair around all."""
+    if flush_bytes:
+        return w.bench_frames(dt, steps, flush_bytes)
+    w.timer_start(); w.step(dt, steps)
+    return w.timer_stop()
+
+
+def parity_check(R, capi):
+    """Sharded world == private 1-GPU world on rank 0's device, byte for byte (the reference's own byte-compare discipline,
+    test/regression/tc-smoke.cmd:30-59).  Both the gathered table (oon_download, every rank) and the shard-local blocks
+    (oon_download_local) are compared."""
+    import numpy as np
+    out = {}
+    cases = (("kat1_exact_equals_1gpu", "c1_kat1", None, capi.MATH_EXACT, 20),
+             ("kat1_fast_equals_1gpu", "c1_kat1", None, capi.MATH_FAST, 20),
+             ("c4_fast_frame_equals_1gpu", "c4_cloud_100k", None, capi.MATH_FAST, 3))
+    for key, workload, n, mode, frames in cases:
+        bodies, cfg = load_workload(workload, n)
+        ws = R.new_world(sharded=True)
+        ws.set_props(**cfg["props"]); ws.math_mode = mode
+        ws.upload(bodies)
+        ws.step(cfg["dt"], frames)
+        got = ws.download()                                   # collective: every rank gets the whole table
+        first, block = ws.download_local()
+        ws.close()
+        ok = True
+        if R.rank == 0:
+            w1 = R.new_world(sharded=False)
+            w1.set_props(**cfg["props"]); w1.math_mode = mode
+            w1.upload(bodies)
+            w1.step(cfg["dt"], frames)
+            ref = w1.download()
+            w1.close()
+            ok = got.tobytes() == ref.tobytes()
+            ref_t = R.torch.from_numpy(np.frombuffer(ref.tobytes(), dtype=np.uint8).copy()).cuda()
+        else:
+            ref_t = R.torch.empty(len(got) * 60, dtype=R.torch.uint8, device="cuda")
+        R.dist.broadcast(ref_t, 0)
+        ref_all = np.frombuffer(ref_t.cpu().numpy().tobytes(), dtype=capi.BODY_F32)
+        ok_local = block.tobytes() == ref_all[first:first + len(block)].tobytes() and got.tobytes() == ref_all.tobytes()
+        out[key] = R.all_true(ok and ok_local)
+    out["what"] = ("sharded world over %d ranks vs a private 1-GPU world on rank 0's device, same input, same frames; oon_download "
+                   "(gathered table, every rank) and oon_download_local (each rank's block) compared byte for byte") % R.size
+    return out
+
+
+def run_c5(R, capi, steps=20, warmup=3):
+    """BASELINE config C5 on all ranks + a short 1-GPU leg of the same world on rank 0's device (same lease, same clocks)."""
+    bodies, cfg = load_workload("c5_void_1m")
+    n, dt = bodies.shape[0], cfg["dt"]
+    w = R.new_world(sharded=True)
+    w.set_props(**cfg["props"])
+    w.upload(bodies)
+    w.step(dt, warmup); w.synchronize()
+    R.barrier()
+    ms = R.max(w.bench_frames(dt, steps, FLUSH_BYTES))
+    R.barrier()
+    _, prof_ms, prof_l = w.bench_frames_profiled(dt, 5, FLUSH_BYTES)
+    k1_ms = R.max(prof_ms["interact"] / max(1, prof_l["interact"]))
+    w.close()
+    rec = {"workload": "c5_void_1m", "n_bodies": n, "n_gpus": R.size, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+           "value": steps * n * (n - 1) / (ms * 1e-3), "unit": "interactions/s", "interact_ms_per_launch_max_over_ranks": k1_ms}
+    one = None
+    if R.rank == 0:
+        w1 = R.new_world(sharded=False)
+        w1.set_props(**cfg["props"])
+        w1.upload(bodies)
+        w1.step(dt, 1); w1.synchronize()
+        ms1 = w1.bench_frames(dt, 3, FLUSH_BYTES) / 3
+        peak = capi.measure_fp32_peak(R.local_rank)
+        w1.close()
+        one = {"ms_per_step": ms1, "value": n * (n - 1) / (ms1 * 1e-3), "steps": 3, "warmup": 1,
+               "where": "rank 0's device, the other ranks idle, same process and lease as the %d-GPU leg" % R.size}
+        rec["one_gpu"] = one
+        rec["efficiency"] = (ms1 / R.size) / (ms / steps)
+        rec["interact_frac_of_fp32_peak"] = FLOP_PER_INTERACTION * (n / R.size) * (n - 1) / (k1_ms * 1e-3) * 1e-12 / peak
+    R.barrier()
+    return rec
+
+
+def run_configs(R, capi):
+    """The other BASELINE configs on one GPU (device time per frame, L2 flushed before every frame): C1 = KAT-1, C2, C3 and the
+    same dense world without mortal bodies (what the sweep machinery costs), FAST and EXACT; C4 in EXACT mode."""
+    out = {}
+    cases = [("c1_kat1", None, False, 200), ("c2_swarm_10k", None, False, 60), ("c3_dense_13k", None, False, 60),
+             ("c3_dense_13k", None, True, 60), ("c4_cloud_100k", None, False, 3)]
+    for workload, n, immortal, steps in cases:
+        bodies, cfg = load_workload(workload, n)
+        if immortal:
+            bodies = bodies.copy(); bodies["lifetime"] = -1.0
+        for mode_name, mode in (("fast", capi.MATH_FAST), ("exact", capi.MATH_EXACT)):
+            if workload == "c4_cloud_100k" and mode_name == "fast":
+                continue                                     # the headline line itself
+            k = steps if mode_name == "fast" or workload == "c1_kat1" else max(3, steps // 6)
+            w = R.new_world(sharded=False)
+            w.set_props(**cfg["props"]); w.math_mode = mode
+            w.upload(bodies)
+            w.step(cfg["dt"], 5); w.synchronize()
+            n0 = w.entity_count()
+            ms = w.bench_frames(cfg["dt"], k, FLUSH_BYTES)
+            n1 = w.entity_count()
+            ev = w.drain_events()
+            w.close()
+            nm = 0.5 * (n0 + n1)
+            out["%s%s/%s" % (workload, "_immortal" if immortal else "", mode_name)] = {
+                "n_bodies": n0, "n_bodies_end": n1, "steps": k, "ms_per_step": ms / k, "steps_per_sec": k / (ms * 1e-3),
+                "value": k * nm * (nm - 1) / (ms * 1e-3), "removed": ev["removed"], "terminated": ev["terminated"]}
+    return out
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import numpy as np
-    import torch
-    import torch.distributed as dist
 
-    from out_of_nothing_b200 import capi, sharding, synth
-    from out_of_nothing_b200.world import World
+    from out_of_nothing_b200 import capi, sharding
 
-    rank = int(os.environ.get("RANK", "0"))
-    world_size = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world_size != args.gpus:
-        if world_size == 1 and args.gpus > 1:
-            print(json.dumps({"error": "--gpus %d needs torchrun with %d ranks" % (args.gpus, args.gpus)}))
-            return 2
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU baseline)")
-    torch.cuda.set_device(local_rank)
-    nccl_id = None
-    if world_size > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        idt = torch.zeros(capi.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(capi.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        nccl_id = bytes(idt.cpu().numpy().tobytes())
+    R = Ranks(args)
+    rank, world_size, local_rank = R.rank, R.size, R.local_rank
+    if world_size != args.gpus and world_size == 1 and args.gpus > 1:
+        print(json.dumps({"error": "--gpus %d needs torchrun with %d ranks" % (args.gpus, args.gpus)}))
+        return 2
+    torch = R.torch
 
-    def barrier():
-        if world_size > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if world_size == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    bodies, cfg = synth.make(args.workload, n=args.n or None)
+    bodies, cfg = load_workload(args.workload, args.n)
     n = bodies.shape[0]
     dt = cfg["dt"]
-    w = World(local_rank, rank, world_size, nccl_id)
+    w = R.new_world(sharded=True)
     w.set_props(**cfg["props"])
     w.math_mode = capi.MATH_EXACT if args.math == "exact" else capi.MATH_FAST
     w.upload(bodies)
 
     # ---- live FP32 peak (roofline denominator) before the run, on this device
     fp32_peak = capi.measure_fp32_peak(local_rank)
+    flush_bytes = 0 if args.no_l2_flush else FLUSH_BYTES
 
-    flush_bytes = 0 if args.no_l2_flush else (256 << 20)     # > 126 MB L2, written on the library's stream before every timed frame
-
-    # ---- warm-up (the clock sampler starts here so that short timed regions still get samples under load)
+    # ---- settle + warm-up.  The clock sampler starts here so that short timed regions still get samples under load.
+    # The first frames after an upload are not the steady state of the frame loop: the slot order of frame k+1 is predicted
+    # from frame k's kicks (none yet), the clocks ramp, and the cloud itself relaxes.  The world is therefore advanced
+    # `settle` frames first (reported, timed separately as "first_frames"), then the caller's W warm-up frames, then K timed ones.
     sampler = ClockSampler(local_rank)
     sampler.start()
     sampler.wait_for_samples(1)
     t_load0 = sampler.mark()
+    settle = args.settle if args.settle >= 0 else (SETTLE_FRAMES if (n >= 32768 and args.math == "fast") else 0)
+    first_ms = None
+    if settle:
+        head = min(settle, 5)
+        first_ms = R.max(timed_frames(w, dt, head, flush_bytes)) / head
+        w.step(dt, settle - head)
     w.step(dt, max(args.warmup, 3))
     w.synchronize()
     n_start = w.entity_count()
 
     # ---- timed region: device time of exactly K frames, barrier + synchronize on both sides, max over ranks
-    barrier()
+    R.barrier()
     launches0 = w.launch_count()
     t_host0 = time.perf_counter()
-    if flush_bytes == 0:
-        w.timer_start(); w.step(dt, args.steps); ms = w.timer_stop()
-    else:
-        ms = w.bench_frames(dt, args.steps, flush_bytes)
-    barrier()
+    ms = timed_frames(w, dt, args.steps, flush_bytes)
+    R.barrier()
     host_s = time.perf_counter() - t_host0
     clocks = sampler.stop(t_load0, time.perf_counter())
     launches = w.launch_count() - launches0
-    ms = max_over_ranks(ms)
+    ms = R.max(ms)
     n_end = w.entity_count()
     inter_per_step = sharding.interactions_per_step(n_start)     # no body of this workload can expire unless it says so
     value = args.steps * inter_per_step / (ms * 1e-3)
@@ -263,30 +425,37 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     k2_gbs = INTEGRATE_BYTES_PER_BODY * (hi - lo) / (k2_ms * 1e-3) * 1e-9 if k2_ms > 0 else 0.0
     traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "interact_traffic.json"))).get(args.workload)
-    except Exception:
-        pass
+    if world_size == 1 and args.math == "fast":              # one ncu --set full capture of a single-GPU launch; a shard's launch was never captured
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "interact_traffic.json"))).get(args.workload)
+        except Exception:
+            pass
 
-    # ---- e2e: the drop-in call sequence with HOST buffers (pinned), copies inside the timed region
+    # ---- e2e: the drop-in call sequence with HOST buffers (pinned), copies inside the timed region.  Every rank keeps the
+    # host table of the reference's `bodies` vector and moves only its own block: oon_upload_local + oon_step + oon_download_local.
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
     host_in = torch.empty(n_start * 60, dtype=torch.uint8).pin_memory()
     host_out = torch.empty(n_start * 60, dtype=torch.uint8).pin_memory()
     cur = w.download()
     host_in.numpy()[:] = np.frombuffer(cur.tobytes(), dtype=np.uint8)
-    w.upload_ptr(host_in.data_ptr(), n_start); w.step(dt, 1); w.download_ptr(host_out.data_ptr(), n_start)   # warm
-    barrier()
+    first, count = w.local_range(n_start)
+
+    def e2e_frame(src, dst):
+        w.upload_local_ptr(src.data_ptr() + first * 60, count, n_start)
+        w.step(dt, 1)
+        return w.download_local_ptr(dst.data_ptr() + first * 60, count)
+
+    e2e_frame(host_in, host_out)                             # warm (allocations of the staging buffers)
+    R.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        w.upload_ptr(host_in.data_ptr(), n_start)
-        w.step(dt, 1)
-        got = w.download_ptr(host_out.data_ptr(), n_start)
+        e2e_frame(host_in, host_out)
         host_in, host_out = host_out, host_in               # next frame's input is this frame's output
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    R.barrier()
+    e2e_s = R.max(time.perf_counter() - t0)
     e2e_value = e2e_steps * sharding.interactions_per_step(n_start) / e2e_s
-    h2d = 60 * n_start                                       # summed over ranks: every rank uploads its own block
-    d2h = 60 * n_start * world_size                          # every rank reads the whole table back
+    h2d = 60 * n_start                                       # summed over ranks: every rank uploads its own block ...
+    d2h = 60 * n_start                                       # ... and reads its own block back
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on one host core, bounded sample
     cpu = None
@@ -301,6 +470,19 @@ def main():
         cpu = {"value": cpu_steps * ns * (ns - 1) / secs, "unit": "interactions/s", "cores": 1, "kind": "port",
                "sample": "first %d bodies of the same world, %d frames, oracle<float> built -O2 -ffp-contract=off, %.1f s" % (ns, cpu_steps, secs)}
 
+    exchange_kind = w.exchange_kind()
+    w.close()
+
+    # ---- sub-records outside the timed region
+    extras = {}
+    if not args.skip_extras and args.workload == "c4_cloud_100k" and args.math == "fast":
+        if world_size > 1:
+            extras["parity_check"] = parity_check(R, capi)
+        if world_size == 8:
+            extras["c5"] = run_c5(R, capi)
+        if world_size == 1:
+            extras["configs"] = run_configs(R, capi)
+
     if rank == 0:
         line = {
             "metric": "body_pair_interactions_per_sec", "value": value, "unit": "interactions/s",
@@ -310,10 +492,15 @@ def main():
             "config": {"workload": args.workload, "n_bodies": n, "n_bodies_end": n_end, "dt": dt, "math": args.math,
                        "parallelism": ("targets sharded in %d contiguous blocks; exchange of the source tiles per frame: %s" % (
                            world_size, {"peer_stores": "pack kernel stores each slice into every peer's buffer over NVLink (CUDA IPC), interact kernel waits on per-slice flags",
-                                        "nccl_allgather": "NCCL all-gather"}[w.exchange_kind()])) if world_size > 1 else "single GPU",
-                       "exchange": w.exchange_kind(),
+                                        "nccl_allgather": "NCCL all-gather"}[exchange_kind])) if world_size > 1 else "single GPU",
+                       "exchange": exchange_kind,
                        "l2": ("flushed before every timed frame (256 MiB device memset on the same stream, outside the per-frame event pairs)"
-                              if flush_bytes else "not flushed; frames timed back to back"), **cfg["props"]},
+                              if flush_bytes else "not flushed; frames timed back to back"),
+                       "settle": ("%d frames advanced after the upload and before the %d warm-up frames (the first frames of a fresh world are not the "
+                                  "steady state of the frame loop: see first_frames)" % (settle, max(args.warmup, 3))) if settle else "none",
+                       **cfg["props"]},
+            "first_frames": ({"ms_per_step": first_ms, "value": inter_per_step / (first_ms * 1e-3), "frames": min(settle, 5),
+                              "what": "the first frames after the upload, same timing recipe"} if first_ms else None),
             "roofline": {"bound": "fp32", "kernel": "k_interact_fast" if args.math == "fast" else "k_interact_exact",
                          "achieved": k1_tflops, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": k1_tflops / fp32_peak if fp32_peak else None, "traffic": traffic,
@@ -327,15 +514,16 @@ def main():
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
-                    "call": "oon_upload(pinned host AoS) + oon_step(dt,1) + oon_download(pinned host AoS) every frame"},
+                    "call": ("oon_upload_local(pinned host AoS, own block) + oon_step(dt,1) + oon_download_local(own block) every frame on every rank"
+                             if world_size > 1 else "oon_upload(pinned host AoS) + oon_step(dt,1) + oon_download(pinned host AoS) every frame")},
             "gpu_launches": launches,
             "clocks": clocks,
             "host_wall_s_timed_region": host_s,
+            **extras,
         }
         print(json.dumps(line), flush=True)
-    w.close()
     if world_size > 1:
-        dist.destroy_process_group()
+        R.dist.destroy_process_group()
     return 0
 
 

@@ -169,6 +169,12 @@ void oracle_phase(void* p, int which, float dt) {
     DISPATCH(h, phase(w, which, dt), phase(w, which, dt));
 }
 
+// the caller's sweep with the app's player index (OON.cpp:1089: `for (i = player_entity_ndx() + 1; ...`)
+void oracle_sweep(void* p, uint64_t player_ndx) {
+    auto* h = static_cast<Handle*>(p);
+    DISPATCH(h, w.sweep_expired(size_t(player_ndx)), w.sweep_expired(size_t(player_ndx)));
+}
+
 void oracle_step(void* p, float dt, uint32_t nsteps, int sweep) {
     auto* h = static_cast<Handle*>(p);
     for (uint32_t k = 0; k < nsteps; ++k) DISPATCH(h, w.step(dt, sweep != 0), w.step(dt, sweep != 0));

@@ -58,6 +58,7 @@ def lib():
         L.oracle_trace_counts.argtypes = [vp, vp]
         L.oracle_trace_fetch.argtypes = [vp, i32, vp]
         L.oracle_phase.argtypes = [vp, i32, f32]
+        L.oracle_sweep.argtypes = [vp, u64]
         L.oracle_step.argtypes = [vp, f32, u32, i32]
         L.oracle_time_steps.restype = f64
         L.oracle_time_steps.argtypes = [vp, f32, u32, i32]
@@ -143,7 +144,7 @@ class OracleWorld:
     def update_intrinsic(self, dt): self.phase(self.INTRINSIC, dt)
     def update_pairwise(self, dt): self.phase(self.PAIRWISE, dt)
     def update_global(self, dt): self.phase(self.GLOBAL, dt)
-    def sweep_expired(self): self.phase(self.SWEEP, 0.0)
+    def sweep_expired(self, player_ndx: int = 0): lib().oracle_sweep(self._h, player_ndx)
 
     #: field order of the 15-float configuration oracle_emit_particles takes (== Emitter::Config, Emitter.hpp:24-37)
     EMITTER_FIELDS = ("eject_velocity_x", "eject_velocity_y", "eject_offset_x", "eject_offset_y", "v_factor", "offset_velo_factor",

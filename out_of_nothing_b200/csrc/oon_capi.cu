@@ -7,6 +7,7 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost nothing unless a tool (nsys, ncu --nvtx) is attached
 
 #include <algorithm>
 #include <utility>
@@ -497,6 +498,15 @@ int begin_pack(oon_world* w, PackOut& out) {
     return OON_OK;
 }
 
+// NVTX range per phase of a frame (pack / interact / integrate / sweep / order), visible in nsys timelines and
+// usable as an ncu filter (--nvtx --nvtx-include "oon/interact/").
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 // Timing scaffold for oon_step_profiled: class -> accumulated ms.  Every kernel class is bracketed by its own event
 // pair on the launching stream; nothing synchronises with the host until the call has enqueued all its frames (a host
 // round trip per kernel would let the ranks of a sharded world drift apart and put launch latency into the numbers).
@@ -622,6 +632,7 @@ int ensure_order(oon_world* w, const StepParams& sp, Prof* prof, bool allow_refr
 // checked instead of 8 %); the prediction misses only the coming kick.  Hiding the sort behind the interact kernel
 // saves ~85 us per frame.
 int start_order_ahead(oon_world* w, const StepParams& sp) {
+    NvtxRange range("oon/order_ahead");
     if (!w->async_sort || w->resort_every != 1 || !wants_morton(w, sp) || w->order_kind != 2 || w->next_order_pending) return OON_OK;
     int rc = ensure_order_buffers(w);
     if (rc) return rc;
@@ -639,6 +650,7 @@ int start_order_ahead(oon_world* w, const StepParams& sp) {
 }
 
 int do_intrinsic_pack(oon_world* w, const StepParams& sp, bool intrinsic, Prof* prof) {
+    NvtxRange range("oon/pack");
     int rc = ensure_order(w, sp, prof);
     if (rc) return rc;
     // The order of the NEXT frame is started here, before this frame's pack and interact kernels are even launched: its
@@ -664,6 +676,7 @@ int do_intrinsic_pack(oon_world* w, const StepParams& sp, bool intrinsic, Prof* 
 }
 
 int do_interact(oon_world* w, const StepParams& sp, Prof* prof) {
+    NvtxRange range("oon/interact");
     InteractGeometry geo{};
     const bool fast_n2n = sp.n2n && !sp.exact;
     int rc;
@@ -709,6 +722,7 @@ int ensure_kick(oon_world* w, const StepParams& sp) {
 }
 
 int do_integrate(oon_world* w, const StepParams& sp, bool apply_pairwise, bool do_global, bool fuse_next, Prof* prof) {
+    NvtxRange range(fuse_next ? "oon/integrate+pack" : "oon/integrate");
     int rc = ensure_kick(w, sp);
     if (rc) return rc;
     if ((rc = ensure_order(w, sp, prof, false))) return rc;
@@ -732,6 +746,7 @@ int do_integrate(oon_world* w, const StepParams& sp, bool apply_pairwise, bool d
 }
 
 int do_sweep(oon_world* w, uint32_t player_ndx, Prof* prof) {
+    NvtxRange range("oon/sweep");
     // Sharded: every rank compacts its own index block (blocks become ragged: fewer bodies than slots); the one thing that
     // crosses ranks is the parity of a run of expired bodies that spans a block boundary.  The player must live on rank 0.
     if (w->nranks > 1 && player_ndx >= w->block) return fail(w, OON_ERR_UNSUPPORTED, "sweep on a sharded world: the player must be on rank 0");
@@ -807,6 +822,7 @@ uint32_t rank_count(const oon_world* w, int g) {
 }
 
 int step_impl(oon_world* w, float dt, uint32_t nsteps, Prof* prof) {
+    NvtxRange range("oon/step");
     if (!nsteps || !w->block) { w->steps += nsteps; return OON_OK; }
     const StepParams sp = step_params(w, dt);
     const bool sweep = w->has_mortals;

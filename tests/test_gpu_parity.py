@@ -257,6 +257,70 @@ def test_fixture_worlds_with_finite_lifetimes_exact(fixture, frames):
         assert ok, (done, field)
 
 
+@pytest.mark.parametrize("mode", [FAST, EXACT])
+def test_sweep_starts_after_the_player_index(mode):
+    """OON.cpp:1089: the sweep tests the bodies AFTER player_entity_ndx(); expired bodies at or before it stay."""
+    bodies = mortal_world()
+    bodies["lifetime"][3:9] = 0.02                     # expire in frame 1, before the player index used below
+    props = dict(friction=0.01, gravity_mode=1, gravity=6.6743e-11, interact_n2n=True, repulsion_stiffness=0.0, collision_mode=1, loop_mode=0)
+    o = make_oracle(bodies, props, trace=True)
+    w = gpu_world(bodies, props, mode, capture=0)
+    w.set_player_index(20)
+    for frame in range(12):
+        if mode == FAST:
+            w.upload(o.bodies())
+        o.trace_clear()
+        o.update_intrinsic(0.033); o.update_pairwise(0.033); o.update_global(0.033); o.sweep_expired(20)
+        w.step(0.033, 1)
+        assert w.entity_count() == o.n, frame
+        assert w.debug_fetch_removed().tolist() == o.trace_fetch()["expired"].tolist(), frame
+        got, ref = w.download(), o.bodies()
+        assert got["lifetime"].tobytes() == ref["lifetime"].tobytes(), frame
+    assert (o.bodies()["lifetime"][:20] == 0).sum() >= 6       # the expired bodies before the player are still there
+    w.close()
+
+
+@pytest.mark.parametrize("mode", [FAST, EXACT])
+@pytest.mark.parametrize("n2n,loop_mode", [(True, 0), (True, 1), (False, 0), (False, 1)])
+def test_player_touch_events_count_touch_hook_calls_with_a_player(kat1, mode, n2n, loop_mode):
+    """snd_clack (World.cpp:537-539): once per touch_hook call when EITHER body is a player — per unordered pair in the
+    half matrix, per ordered visit in the full matrix, per (0, j) pair in player-only mode.  Every 7th body gets thrusters."""
+    start, _ = kat1
+    bodies = start.bodies.copy()
+    bodies["thrust"][::7] = 0.0
+    bodies["p"][1:40] = bodies["p"][0] + (bodies["r"][0] + bodies["r"][1:40])[:, None] * np.array([[0.5994, 0.7992]], np.float32)   # just inside touching distance of body 0
+    props = smoke_props(start, interact_n2n=n2n, loop_mode=loop_mode)
+    o = make_oracle(bodies, props, trace=True)
+    w = gpu_world(bodies, props, mode, capture=1 << 16)
+    o.step(DT, 1); w.step(DT, 1)
+    tr = o.trace_fetch()
+    player = bodies["thrust"][:, 0] != np.float32(2e31)
+    expect = int(sum(1 for t, s_ in tr["touches"].tolist() if player[t] or player[s_]))
+    ev = w.drain_events()
+    assert len(tr["touches"]) > 20 and expect > 5
+    assert ev["touches"] == len(tr["touches"]) and ev["player_touches"] == expect, (ev, len(tr["touches"]), expect)
+    assert (w.download()["T"] == o.bodies()["T"]).all()
+    w.close()
+
+
+def test_shard_local_io_on_one_gpu_equals_upload_download(kat1):
+    start, _ = kat1
+    w = gpu_world(start.bodies, smoke_props(start), FAST, capture=0)
+    n = w.entity_count()
+    assert w.local_range(n) == (0, n)
+    w.step(DT, 2)
+    first, block = w.download_local()
+    assert first == 0 and block.tobytes() == w.download().tobytes()
+    w.upload_local(block, n)
+    w.step(DT, 1)
+    a = w.download()
+    w2 = gpu_world(block, smoke_props(start), FAST, capture=0); w2.step(DT, 1)
+    assert a.tobytes() == w2.download().tobytes()
+    with pytest.raises(capi.OonError):
+        w.upload_local(block[:-1], n)                    # a block of the wrong size is refused
+    w.close(); w2.close()
+
+
 # ---------------------------------------------------------------------------------------------- sizes and edges
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 31, 255, 256, 257, 511, 513, 1500])
 def test_ragged_and_tiny_worlds(n):
