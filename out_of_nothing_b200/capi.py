@@ -75,9 +75,9 @@ class Events(ctypes.Structure):
 
 #: every symbol include/oon_gpu.h declares (tests check the library exports exactly these)
 EXPORTS = [
-    "oon_abi_version", "oon_create", "oon_nccl_unique_id", "oon_create_sharded", "oon_destroy", "oon_last_error",
+    "oon_abi_version", "oon_create", "oon_nccl_unique_id", "oon_create_sharded", "oon_create_multi", "oon_device_count", "oon_destroy", "oon_last_error",
     "oon_props_default", "oon_set_props", "oon_get_props", "oon_set_math_mode", "oon_get_math_mode",
-    "oon_upload", "oon_upload_f64", "oon_shard_range", "oon_upload_local", "oon_download_local", "oon_set_player_index", "oon_download", "oon_download_f64", "oon_download_render", "oon_download_render_begin", "oon_download_render_end", "oon_body_count",
+    "oon_upload", "oon_upload_f64", "oon_shard_range", "oon_upload_local", "oon_download_local", "oon_set_player_index", "oon_download", "oon_download_f64", "oon_download_render", "oon_download_render_rgb", "oon_download_render_begin", "oon_download_render_end", "oon_body_count",
     "oon_add_bodies", "oon_remove_body", "oon_get_body", "oon_set_body", "oon_emitter_cfg_default", "oon_emit_particles", "oon_chemtrail_burst", "oon_spawn",
     "oon_step", "oon_update_intrinsic", "oon_update_pairwise", "oon_update_global", "oon_sweep_expired",
     "oon_synchronize", "oon_drain_events",
@@ -109,6 +109,8 @@ def load():
     L.oon_create.argtypes = [i32, P(vp)]
     L.oon_nccl_unique_id.argtypes = [vp]
     L.oon_create_sharded.argtypes = [i32, i32, i32, vp, P(vp)]
+    L.oon_create_multi.argtypes = [P(i32), i32, P(vp)]
+    L.oon_device_count.argtypes = [vp, P(i32)]
     L.oon_destroy.argtypes = [vp]
     L.oon_last_error.restype = ctypes.c_char_p
     L.oon_last_error.argtypes = [vp]
@@ -126,6 +128,7 @@ def load():
     L.oon_set_player_index.argtypes = [vp, u64]
     L.oon_download_f64.argtypes = [vp, vp, u64, P(u64)]
     L.oon_download_render.argtypes = [vp, vp, u64, P(u64)]
+    L.oon_download_render_rgb.argtypes = [vp, vp, vp, u64, P(u64)]
     L.oon_body_count.argtypes = [vp, P(u64)]
     L.oon_add_bodies.argtypes = [vp, vp, u64]
     L.oon_remove_body.argtypes = [vp, u64]

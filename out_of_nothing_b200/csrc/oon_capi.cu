@@ -68,6 +68,17 @@ struct SoAStorage {
 };
 
 struct oon_world {
+    // A handle is one of three things:
+    //   * one world on one GPU (nranks == 1),
+    //   * one shard of a world sharded over nranks PROCESSES (oon_create_sharded: comm != nullptr, collectives through NCCL),
+    //   * a GROUP (oon_create_multi): one process, one host thread, kids.size() GPUs.  The group handle itself owns no
+    //     device state; its children are ordinary shards (rank g of kids.size()) whose collectives are done in-process:
+    //     peer-access pointers instead of CUDA IPC, cross-stream events + peer copies instead of NCCL.
+    // Every entry point works on the TEAM of shards the calling thread drives: {this} or kids.
+    std::vector<oon_world*> kids;      // group handle only
+    oon_world* parent = nullptr;       // child of a group handle
+    std::vector<oon_world*> team;      // {this} for a plain handle, kids for a group handle
+    cudaEvent_t ev_grp = nullptr, ev_grp_done = nullptr;   // in-process collectives of a group (record / consumed)
     int device = 0;
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
@@ -82,6 +93,7 @@ struct oon_world {
     uint32_t block = 0;       // slots per rank (multiple of TS); slots == block
     uint32_t cblock = 0;      // bodies per canonical block (block == cblock * 8 / nranks)
     uint32_t n_local = 0;     // host view of the live local count
+    bool counts_stale = false; // a sweep ran on the device since the host last learnt the counts
     bool has_mortals = false; // any body with lifetime > 0 or a non-unlimited non-positive lifetime
     uint32_t player_ndx = 0;  // player_entity_ndx(): the sweep inside oon_step tests the bodies after it (OON.cpp:1089)
 
@@ -118,7 +130,8 @@ struct oon_world {
     uint32_t* d_removed_count = nullptr;
     int* runinfo = nullptr;                              // sharded sweep: [nranks][4] {bodies, trailing expired run, whole block one run, -}
     uint32_t* d_counts = nullptr;                        // sharded: live bodies of every rank (device), counts[] = host copy
-    std::vector<uint32_t> counts;
+    std::vector<uint32_t> counts;                        // sharded: bodies of every rank as the host last learnt them (authoritative unless counts_stale)
+    EmitBase* emit_rec = nullptr;                        // [nranks] records of the body-creating loops (emitter / parent / result)
     unsigned long long* counters = nullptr;   // C_COUNT
     void* sweep_temp = nullptr; size_t sweep_temp_bytes = 0;
     int* sweep_scratch = nullptr; uint32_t sweep_scratch_cap = 0;
@@ -161,14 +174,20 @@ namespace {
 int fail(oon_world* w, int code, const char* fmt, ...) {
     char buf[512];
     va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
-    if (w) { w->error = buf; if (code == OON_ERR_CUDA || code == OON_ERR_NCCL) w->sticky = code; }
-    else g_create_error = buf;
+    if (w) {
+        w->error = buf;
+        if (code == OON_ERR_CUDA || code == OON_ERR_NCCL) w->sticky = code;
+        if (w->parent) { w->parent->error = buf; if (w->sticky != OON_OK) w->parent->sticky = w->sticky; }   // the caller holds the group handle
+    } else g_create_error = buf;
     return code;
 }
 
 #define CU(w, call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(w, OON_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
 #define NC(w, call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) return fail(w, OON_ERR_NCCL, "%s failed: %s", #call, g_nccl.GetErrorString(r_)); } while (0)
-#define CHECK_W(w) do { if (!(w)) return OON_ERR_INVALID; if ((w)->sticky != OON_OK) return (w)->sticky; if (cudaSetDevice((w)->device) != cudaSuccess) return fail(w, OON_ERR_CUDA, "cudaSetDevice(%d) failed", (w)->device); } while (0)
+#define CHECK_W(w) do { if (!(w)) return OON_ERR_INVALID; if ((w)->sticky != OON_OK) return (w)->sticky; if ((w)->kids.empty() && cudaSetDevice((w)->device) != cudaSuccess) return fail(w, OON_ERR_CUDA, "cudaSetDevice(%d) failed", (w)->device); } while (0)
+// make shard m's device current (a team of a group handle spans several devices; a plain handle's device was set by CHECK_W)
+#define USE(m) do { if ((m)->parent && cudaSetDevice((m)->device) != cudaSuccess) return fail(m, OON_ERR_CUDA, "cudaSetDevice(%d) failed", (m)->device); } while (0)
+inline bool in_group(const oon_world* m) { return m->parent != nullptr; }
 
 // Wait for the main stream, then look at the peer-to-peer exchange's time-out word (mapped host memory the kernels bump
 // when a wait for a peer's slice gives up): a kernel that carried on without a slice has produced garbage and has broken
@@ -229,7 +248,10 @@ int soa_copy(oon_world* w, SoAStorage& dst, const SoAStorage& src, uint32_t n) {
 uint32_t round_up(uint64_t x, uint32_t m) { return uint32_t((x + m - 1) / m * m); }
 
 // ---- peer-to-peer exchange plumbing ------------------------------------------------------------------------------
-// Host-level rendezvous of the ranks: a one-word all-gather, then wait for it.
+typedef std::vector<oon_world*> Team;
+
+// Host-level rendezvous of the ranks of a multi-process world: a one-word all-gather, then wait for it.  (The shards of a
+// group are driven by one host thread: synchronising their streams IS the rendezvous.)
 int barrier(oon_world* w) {
     if (w->nranks == 1 || !w->comm) return OON_OK;
     NC(w, g_nccl.AllGather(static_cast<char*>(w->ipc_stage) + size_t(w->rank) * 4, w->ipc_stage, 4, ncclChar, w->comm, w->stream));
@@ -240,7 +262,7 @@ int barrier(oon_world* w) {
 void p2p_close_tiles(oon_world* w) {
     for (int b = 0; b < 2; ++b)
         for (int g = 0; g < 8; ++g)
-            if (w->peer_tiles[b][g]) { cudaIpcCloseMemHandle(w->peer_tiles[b][g]); w->peer_tiles[b][g] = nullptr; }
+            if (w->peer_tiles[b][g]) { if (!in_group(w)) cudaIpcCloseMemHandle(w->peer_tiles[b][g]); w->peer_tiles[b][g] = nullptr; }
 }
 
 struct IpcMsg {
@@ -251,9 +273,9 @@ struct IpcMsg {
 };
 static_assert(sizeof(IpcMsg) == 256, "IpcMsg is one 256-byte row of the staging buffer");
 
-// Export this rank's two exchange buffers (and, once, its flag array), import everybody else's.  Every rank reaches the
-// same verdict: if any export or import fails anywhere (no peer access, different nodes, two ranks in one process...)
-// all ranks fall back to the NCCL all-gather.
+// Multi-process world: export this rank's two exchange buffers (and, once, its flag array), import everybody else's.  Every
+// rank reaches the same verdict: if any export or import fails anywhere (no peer access, different nodes, two ranks in one
+// process...) all ranks fall back to the NCCL all-gather.
 int p2p_open(oon_world* w) {
     w->p2p = false;
     if (w->nranks < 2 || w->nranks > 8 || !w->p2p_wanted) return OON_OK;
@@ -304,42 +326,58 @@ int p2p_open(oon_world* w) {
     return OON_OK;
 }
 
-// (Re)allocate the exchange buffer(s) for `need_slots` slots.  Collective on sharded worlds (every rank lays the
-// same world out at the same time).
-int realloc_exchange(oon_world* w, size_t need_slots) {
-    SYNC(w);
-    if (w->p2p) {
+// (Re)allocate the exchange buffers of every shard of the team for `need_slots` slots and connect the peers again.
+// Collective on multi-process worlds (every rank lays the same world out at the same time).
+int team_realloc_exchange(Team& T, size_t need_slots) {
+    int rc;
+    for (oon_world* w : T) { USE(w); SYNC(w); }            // no kernel of this team still stores into a buffer about to go
+    for (oon_world* w : T) {
+        if (!w->p2p) continue;
         p2p_close_tiles(w);
-        int rc = barrier(w);                               // every peer has unmapped my buffers before I free them
-        if (rc) return rc;
+        if (!in_group(w) && (rc = barrier(w))) return rc;  // multi-process: every peer has unmapped my buffers before I free them
         w->p2p = false;
     }
-    cudaFree(w->tiles_buf[0]); cudaFree(w->tiles_buf[1]); cudaFree(w->scratch4);
-    w->tiles_buf[0] = w->tiles_buf[1] = w->tiles = nullptr; w->scratch4 = nullptr; w->tiles_cap_slots = 0;
-    const bool try_p2p = w->nranks >= 2 && w->nranks <= 8 && w->p2p_wanted;
-    int rc = dev_alloc(w, &w->tiles_buf[0], need_slots / TS * TILE_FLOATS);
-    if (rc) return rc;
-    if (try_p2p && (rc = dev_alloc(w, &w->tiles_buf[1], need_slots / TS * TILE_FLOATS))) return rc;
-    if ((rc = dev_alloc(w, &w->scratch4, need_slots))) return rc;
-    w->tiles = w->tiles_buf[0];
-    w->tiles_cap_slots = need_slots;
-    if (try_p2p && (rc = p2p_open(w))) return rc;
-    if (w->p2p) w->tiles = w->tiles_buf[w->epoch & 1u];
+    for (oon_world* w : T) {
+        USE(w);
+        cudaFree(w->tiles_buf[0]); cudaFree(w->tiles_buf[1]); cudaFree(w->scratch4);
+        w->tiles_buf[0] = w->tiles_buf[1] = w->tiles = nullptr; w->scratch4 = nullptr; w->tiles_cap_slots = 0;
+        const bool two = in_group(w) || (w->nranks >= 2 && w->nranks <= 8 && w->p2p_wanted);
+        if ((rc = dev_alloc(w, &w->tiles_buf[0], need_slots / TS * TILE_FLOATS))) return rc;
+        if (two && (rc = dev_alloc(w, &w->tiles_buf[1], need_slots / TS * TILE_FLOATS))) return rc;
+        if ((rc = dev_alloc(w, &w->scratch4, need_slots))) return rc;
+        w->tiles = w->tiles_buf[0];
+        w->tiles_cap_slots = need_slots;
+    }
+    for (oon_world* w : T) {
+        if (in_group(w)) {                                 // group: the peers' buffers are plain peer-access pointers
+            for (oon_world* g : T) {
+                if (g == w) continue;
+                w->peer_tiles[0][g->rank] = g->tiles_buf[0]; w->peer_tiles[1][g->rank] = g->tiles_buf[1];
+                w->peer_flags[g->rank] = g->flags;
+            }
+            w->p2p = true;
+        } else if (w->nranks >= 2 && w->nranks <= 8 && w->p2p_wanted) {
+            USE(w);
+            if ((rc = p2p_open(w))) return rc;
+        }
+        if (w->p2p) w->tiles = w->tiles_buf[w->epoch & 1u];
+    }
     return OON_OK;
 }
 
-// Lay the world out for `n_total` bodies: block size, SoA capacity, exchange buffer.  Keeps the first
-// `keep` local bodies of the current SoA.
-int layout(oon_world* w, uint64_t n_total, uint32_t keep) {
+// Lay one shard out for a world with room for `n_cap` bodies of which `n_present` exist now (spread over the ranks by
+// block boundaries): block size, SoA capacity, accumulators, order buffers.  Keeps the first `keep` local bodies of the
+// current SoA.  *need_slots_out = slots the exchange buffer must be re-allocated for (0: it is large enough).
+int layout_one(oon_world* w, uint64_t n_cap, uint64_t n_present, uint32_t keep, size_t* need_slots_out) {
     // Canonical blocks: 1/8 of the world each, whatever the number of GPUs; a rank owns 8/nranks of them.  (Other
     // rank counts fall back to one block per rank: still correct, but their sums differ in the last bits from 1/2/4/8.)
     const bool canon = (w->nranks == 1 || w->nranks == 2 || w->nranks == 4 || w->nranks == 8);
     const uint32_t nblocks = canon ? 8u : uint32_t(w->nranks);
-    const uint32_t cblock = std::max<uint32_t>(TS, round_up((n_total + nblocks - 1) / nblocks, TS));
+    const uint32_t cblock = std::max<uint32_t>(TS, round_up((n_cap + nblocks - 1) / nblocks, TS));
     const uint32_t block = cblock * (nblocks / uint32_t(w->nranks));
     w->cblock = cblock;
     if (uint64_t(block) * w->nranks > 0x40000000ull)   // 2^22 tiles: the carry-save limbs take that many addends
-        return fail(w, OON_ERR_INVALID, "world too large: %llu bodies", (unsigned long long)n_total);
+        return fail(w, OON_ERR_INVALID, "world too large: %llu bodies", (unsigned long long)n_cap);
     if (block > w->soa[w->cur].cap) {
         // a single-GPU world gets head-room so that add_bodies rarely reallocates
         const uint32_t cap = w->nranks == 1 ? round_up(uint64_t(block) + block / 2, TS) : block;
@@ -353,10 +391,7 @@ int layout(oon_world* w, uint64_t n_total, uint32_t keep) {
     }
     // exchange buffer (+ the player-only reaction scratch, one float4 per slot)
     const size_t need_slots = size_t(w->nranks) * (w->nranks == 1 ? w->soa[w->cur].cap : block);
-    if (need_slots > w->tiles_cap_slots) {
-        int rc = realloc_exchange(w, need_slots);
-        if (rc) return rc;
-    }
+    *need_slots_out = need_slots > w->tiles_cap_slots ? need_slots : 0;
     // exact accumulators of the FAST all-pairs kernel, zero between passes
     if (w->soa[w->cur].cap > w->acc_cap) {
         cudaFree(w->acc); cudaFree(w->touch); w->acc = nullptr; w->touch = nullptr; w->acc_cap = 0;
@@ -375,16 +410,36 @@ int layout(oon_world* w, uint64_t n_total, uint32_t keep) {
         if ((rc = dev_alloc(w, &w->inv_next, w->soa[w->cur].cap))) return rc;
         w->inv_cap = w->soa[w->cur].cap;
     }
-    if (block != w->block || n_total != w->n_total) {   // same table shape: a stale order is still a valid (if less tight) order
+    if (block != w->block || n_present != w->n_total) {   // same table shape: a stale order is still a valid (if less tight) order
         w->order_dirty = true;
         w->kick_valid = false;
     }
     w->block = block;
-    w->n_total = n_total;
+    w->n_total = n_present;
     const uint64_t lo = uint64_t(w->rank) * block;
-    w->n_local = n_total > lo ? uint32_t(std::min<uint64_t>(block, n_total - lo)) : 0u;
+    w->n_local = n_present > lo ? uint32_t(std::min<uint64_t>(block, n_present - lo)) : 0u;
+    for (int g = 0; g < w->nranks && !w->counts.empty(); ++g) {          // the even split, until sweeps and edits make the blocks ragged
+        const uint64_t glo = uint64_t(g) * block;
+        w->counts[size_t(g)] = n_present > glo ? uint32_t(std::min<uint64_t>(block, n_present - glo)) : 0u;
+    }
+    w->counts_stale = false;
     w->tiles_fresh = false;
     return OON_OK;
+}
+
+// keep_local: keep every shard's current local bodies (growing a world in place) instead of starting from an empty table
+int team_layout(Team& T, uint64_t n_cap, uint64_t n_present, bool keep_local) {
+    size_t need = 0;
+    for (oon_world* w : T) {
+        USE(w);
+        size_t nm = 0;
+        const uint32_t keep = keep_local ? w->n_local : 0u;
+        int rc = layout_one(w, n_cap, n_present, keep, &nm);
+        if (rc) return rc;
+        if (keep_local) w->n_local = keep;
+        need = std::max(need, nm);
+    }
+    return need ? team_realloc_exchange(T, need) : OON_OK;
 }
 
 uint32_t total_tiles(const oon_world* w) { return uint32_t(uint64_t(w->block) * w->nranks / TS); }
@@ -745,103 +800,168 @@ int do_integrate(oon_world* w, const StepParams& sp, bool apply_pairwise, bool d
     return OON_OK;
 }
 
-int do_sweep(oon_world* w, uint32_t player_ndx, Prof* prof) {
-    NvtxRange range("oon/sweep");
-    // Sharded: every rank compacts its own index block (blocks become ragged: fewer bodies than slots); the one thing that
-    // crosses ranks is the parity of a run of expired bodies that spans a block boundary.  The player must live on rank 0.
-    if (w->nranks > 1 && player_ndx >= w->block) return fail(w, OON_ERR_UNSUPPORTED, "sweep on a sharded world: the player must be on rank 0");
-    const uint32_t slots = w->block;
-    SoAStorage& other = w->soa[w->cur ^ 1];
-    if (other.cap < w->soa[w->cur].cap) { int rc = soa_alloc(w, other, w->soa[w->cur].cap); if (rc) return rc; }
-    const size_t tb = sweep_temp_bytes(w->soa[w->cur].cap);
-    if (tb > w->sweep_temp_bytes) {
-        cudaFree(w->sweep_temp); w->sweep_temp = nullptr;
-        CU(w, cudaMalloc(&w->sweep_temp, tb)); w->sweep_temp_bytes = tb;
+// ---- in-process collectives of a group ------------------------------------------------------------------------------
+// "Every shard has produced its record on its own stream; every shard now needs all of them": each shard records an event
+// after producing, waits for the peers' events and pulls their records with peer copies on its own stream.  The events of
+// the previous use (ev_grp_done) keep a producer from overwriting a record a peer is still reading.
+int group_before_produce(Team& T) {
+    for (oon_world* m : T) {
+        USE(m);
+        for (oon_world* g : T) if (g != m) CU(m, cudaStreamWaitEvent(m->stream, g->ev_grp_done, 0));
     }
-    if (w->sweep_scratch_cap < w->soa[w->cur].cap) {
-        cudaFree(w->sweep_scratch); w->sweep_scratch = nullptr;
-        int rc = dev_alloc(w, &w->sweep_scratch, size_t(3) * w->soa[w->cur].cap); if (rc) return rc;
-        w->sweep_scratch_cap = w->soa[w->cur].cap;
-    }
-    if (w->removed_cap < w->soa[w->cur].cap) {
-        cudaFree(w->removed_idx); w->removed_idx = nullptr;
-        int rc = dev_alloc(w, &w->removed_idx, w->soa[w->cur].cap); if (rc) return rc;
-        w->removed_cap = w->soa[w->cur].cap;
-    }
-    const uint32_t first_tested = w->rank == 0 ? player_ndx + 1 : 0u;
-    int rc = timed(w, prof, 3, [&](int& launched) -> int {
-        CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));
-        launched = launch_sweep_scan(w->stream, w->soa[w->cur].d, w->d_n, slots, first_tested, w->sweep_temp, w->sweep_temp_bytes,
-                                     w->sweep_scratch, w->nranks > 1 ? w->runinfo + 4 * w->rank : nullptr);
-        CU(w, cudaGetLastError());
-        if (w->nranks > 1) {
-            NC(w, g_nccl.AllGather(w->runinfo + 4 * w->rank, w->runinfo, 4, ncclInt32, w->comm, w->stream));
-            ++launched;
+    return OON_OK;
+}
+template <class ArrOf>
+int group_allgather(Team& T, ArrOf arr_of, size_t bytes_per_rank) {
+    for (oon_world* m : T) { USE(m); CU(m, cudaEventRecord(m->ev_grp, m->stream)); }
+    for (oon_world* m : T) {
+        USE(m);
+        for (oon_world* g : T) {
+            if (g == m) continue;
+            CU(m, cudaStreamWaitEvent(m->stream, g->ev_grp, 0));
+            CU(m, cudaMemcpyPeerAsync(arr_of(m) + size_t(g->rank) * bytes_per_rank, m->device, arr_of(g) + size_t(g->rank) * bytes_per_rank, g->device,
+                                      bytes_per_rank, m->stream));
         }
-        launched += launch_sweep_compact(w->stream, w->soa[w->cur].d, other.d, w->d_n, slots, w->nranks > 1 ? w->runinfo : nullptr, w->rank,
-                                         w->sweep_temp, w->sweep_temp_bytes, w->sweep_scratch, w->removed_idx, w->removed_cap,
-                                         w->d_removed_count, w->counters);
-        CU(w, cudaGetLastError());
-        return OON_OK;
-    });
-    if (rc) return rc;
-    w->cur ^= 1;
-    w->tiles_fresh = false;
-    w->order_dirty = true;          // indices shifted
+        CU(m, cudaEventRecord(m->ev_grp_done, m->stream));
+    }
+    return OON_OK;
+}
+// Stream-ordered all-gather of one small record per rank, whatever kind of team: NCCL between processes, peer copies in a group.
+template <class ArrOf>
+int team_allgather(Team& T, ArrOf arr_of, size_t bytes_per_rank) {
+    if (T.size() > 1) return group_allgather(T, arr_of, bytes_per_rank);
+    oon_world* w = T[0];
+    if (w->nranks == 1) return OON_OK;
+    NC(w, g_nccl.AllGather(arr_of(w) + size_t(w->rank) * bytes_per_rank, arr_of(w), bytes_per_rank, ncclChar, w->comm, w->stream));
     return OON_OK;
 }
 
-// Refresh the host's idea of the body count after device-side removals.
-int sync_count(oon_world* w) {
-    if (!w->has_mortals) return OON_OK;
-    if (w->nranks == 1) {
+// The caller's expired-body sweep (OON.cpp:1089-1095) for the whole team.  Sharded: every rank compacts its own index block
+// (blocks become ragged: fewer bodies than slots); the one thing that crosses ranks is the parity of a run of expired bodies
+// that spans a block boundary: one 16-byte record per rank, all-gathered between the scan and the compaction.  The player
+// must live on rank 0.
+int team_sweep(Team& T, uint32_t player_ndx, std::vector<Prof>* profs) {
+    NvtxRange range("oon/sweep");
+    int rc;
+    if (T.size() > 1 && (rc = group_before_produce(T))) return rc;
+    for (size_t i = 0; i < T.size(); ++i) {
+        oon_world* w = T[i];
+        USE(w);
+        if (w->nranks > 1 && player_ndx >= w->block) return fail(w, OON_ERR_UNSUPPORTED, "sweep on a sharded world: the player must be on rank 0");
+        SoAStorage& other = w->soa[w->cur ^ 1];
+        if (other.cap < w->soa[w->cur].cap) { if ((rc = soa_alloc(w, other, w->soa[w->cur].cap))) return rc; }
+        const size_t tb = sweep_temp_bytes(w->soa[w->cur].cap);
+        if (tb > w->sweep_temp_bytes) {
+            cudaFree(w->sweep_temp); w->sweep_temp = nullptr;
+            CU(w, cudaMalloc(&w->sweep_temp, tb)); w->sweep_temp_bytes = tb;
+        }
+        if (w->sweep_scratch_cap < w->soa[w->cur].cap) {
+            cudaFree(w->sweep_scratch); w->sweep_scratch = nullptr;
+            if ((rc = dev_alloc(w, &w->sweep_scratch, size_t(3) * w->soa[w->cur].cap))) return rc;
+            w->sweep_scratch_cap = w->soa[w->cur].cap;
+        }
+        if (w->removed_cap < w->soa[w->cur].cap) {
+            cudaFree(w->removed_idx); w->removed_idx = nullptr;
+            if ((rc = dev_alloc(w, &w->removed_idx, w->soa[w->cur].cap))) return rc;
+            w->removed_cap = w->soa[w->cur].cap;
+        }
+        const uint32_t first_tested = w->rank == 0 ? player_ndx + 1 : 0u;
+        rc = timed(w, profs ? &(*profs)[i] : nullptr, 3, [&](int& launched) -> int {
+            CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));
+            launched = launch_sweep_scan(w->stream, w->soa[w->cur].d, w->d_n, w->block, first_tested, w->sweep_temp, w->sweep_temp_bytes,
+                                         w->sweep_scratch, w->nranks > 1 ? w->runinfo + 4 * w->rank : nullptr);
+            CU(w, cudaGetLastError());
+            return OON_OK;
+        });
+        if (rc) return rc;
+    }
+    if ((rc = team_allgather(T, [](oon_world* m) { return reinterpret_cast<char*>(m->runinfo); }, 4 * sizeof(int)))) return rc;
+    for (size_t i = 0; i < T.size(); ++i) {
+        oon_world* w = T[i];
+        USE(w);
+        rc = timed(w, profs ? &(*profs)[i] : nullptr, 3, [&](int& launched) -> int {
+            launched = (w->nranks > 1 ? 1 : 0) +
+                       launch_sweep_compact(w->stream, w->soa[w->cur].d, w->soa[w->cur ^ 1].d, w->d_n, w->block, w->nranks > 1 ? w->runinfo : nullptr, w->rank,
+                                            w->sweep_temp, w->sweep_temp_bytes, w->sweep_scratch, w->removed_idx, w->removed_cap,
+                                            w->d_removed_count, w->counters);
+            CU(w, cudaGetLastError());
+            return OON_OK;
+        });
+        if (rc) return rc;
+        w->cur ^= 1;
+        w->tiles_fresh = false;
+        w->order_dirty = true;          // indices shifted
+        w->counts_stale = true;
+    }
+    return OON_OK;
+}
+
+// Refresh the host's idea of the body counts after device-side removals (sweeps).
+int team_sync_count(Team& T) {
+    bool stale = false;
+    for (oon_world* w : T) stale = stale || w->counts_stale;
+    if (!stale) return OON_OK;
+    oon_world* w0 = T[0];
+    if (w0->nranks == 1) {
         uint32_t n = 0;
-        CU(w, cudaMemcpyAsync(&n, w->d_n, sizeof n, cudaMemcpyDeviceToHost, w->stream));
-        SYNC(w);
-        w->n_local = n;
-        w->n_total = n;
+        CU(w0, cudaMemcpyAsync(&n, w0->d_n, sizeof n, cudaMemcpyDeviceToHost, w0->stream));
+        SYNC(w0);
+        w0->n_local = n;
+        w0->n_total = n;
+        w0->counts_stale = false;
         return OON_OK;
     }
-    // sharded: the ranks' blocks are ragged after a sweep — everybody learns everybody's count
-    CU(w, cudaMemcpyAsync(w->d_counts + w->rank, w->d_n, sizeof(uint32_t), cudaMemcpyDeviceToDevice, w->stream));
-    NC(w, g_nccl.AllGather(w->d_counts + w->rank, w->d_counts, 1, ncclUint32, w->comm, w->stream));
-    CU(w, cudaMemcpyAsync(w->counts.data(), w->d_counts, sizeof(uint32_t) * size_t(w->nranks), cudaMemcpyDeviceToHost, w->stream));
-    SYNC(w);
-    w->n_local = w->counts[size_t(w->rank)];
+    std::vector<uint32_t> counts(size_t(w0->nranks), 0u);
+    if (T.size() > 1) {                                     // group: the host reads every shard's count itself
+        for (oon_world* w : T) { USE(w); CU(w, cudaMemcpyAsync(&counts[size_t(w->rank)], w->d_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream)); }
+        for (oon_world* w : T) { USE(w); SYNC(w); }
+    } else {                                                // one rank of a multi-process world: everybody learns everybody's count
+        CU(w0, cudaMemcpyAsync(w0->d_counts + w0->rank, w0->d_n, sizeof(uint32_t), cudaMemcpyDeviceToDevice, w0->stream));
+        NC(w0, g_nccl.AllGather(w0->d_counts + w0->rank, w0->d_counts, 1, ncclUint32, w0->comm, w0->stream));
+        CU(w0, cudaMemcpyAsync(counts.data(), w0->d_counts, sizeof(uint32_t) * counts.size(), cudaMemcpyDeviceToHost, w0->stream));
+        SYNC(w0);
+    }
     uint64_t total = 0;
-    for (uint32_t c : w->counts) total += c;
-    w->n_total = total;
+    for (uint32_t c : counts) total += c;
+    for (oon_world* w : T) {
+        w->counts = counts;
+        w->n_local = counts[size_t(w->rank)];
+        w->n_total = total;
+        w->counts_stale = false;
+    }
     return OON_OK;
 }
 
-// Bodies of rank g as the host last learnt them: the even split after an upload, the gathered counts once bodies can expire.
-uint32_t rank_count(const oon_world* w, int g) {
-    if (w->nranks > 1 && w->has_mortals && !w->counts.empty()) return w->counts[size_t(g)];
-    const uint64_t lo = uint64_t(g) * w->block;
-    return w->n_total > lo ? uint32_t(std::min<uint64_t>(w->block, w->n_total - lo)) : 0u;
-}
+// Bodies of rank g as the host last learnt them (call team_sync_count first).
+uint32_t rank_count(const oon_world* w, int g) { return w->nranks == 1 ? w->n_local : w->counts[size_t(g)]; }
+uint64_t rank_first(const oon_world* w, int g) { uint64_t f = 0; for (int h = 0; h < g; ++h) f += rank_count(w, h); return f; }
 
-int step_impl(oon_world* w, float dt, uint32_t nsteps, Prof* prof) {
+// nsteps frames for every shard of the team, phase by phase: all packs are enqueued before the first interact kernel that
+// waits for them (a group's shards wait for each other's flags ON THE DEVICE; the single host thread must never block on a
+// kernel whose peers' producers it has not enqueued yet).
+int team_step(Team& T, float dt, uint32_t nsteps, std::vector<Prof>* profs) {
     NvtxRange range("oon/step");
-    if (!nsteps || !w->block) { w->steps += nsteps; return OON_OK; }
-    const StepParams sp = step_params(w, dt);
-    const bool sweep = w->has_mortals;
-    // Frame k: intrinsic+pack -> (all-gather) -> interact -> integrate.  Without mortal bodies the integrate kernel of
+    oon_world* w0 = T[0];
+    if (!nsteps || !w0->block) { for (oon_world* w : T) w->steps += nsteps; return OON_OK; }
+    const StepParams sp = step_params(w0, dt);
+    const bool sweep = w0->has_mortals;
+    auto prof_of = [&](size_t i) { return profs ? &(*profs)[i] : nullptr; };
+    int rc;
+    // Frame k: intrinsic+pack -> (exchange) -> interact -> integrate.  Without mortal bodies the integrate kernel of
     // frame k also runs frame k+1's intrinsic+pack (one pass over the SoA, one launch) unless the slot order is due
     // for a refresh.
-    int rc = do_intrinsic_pack(w, sp, true, prof);
-    if (rc) return rc;
+    for (size_t i = 0; i < T.size(); ++i) { USE(T[i]); if ((rc = do_intrinsic_pack(T[i], sp, true, prof_of(i)))) return rc; }
     for (uint32_t k = 0; k < nsteps; ++k) {
-        if ((rc = do_interact(w, sp, prof))) return rc;
-        ++w->order_age;
+        for (size_t i = 0; i < T.size(); ++i) { USE(T[i]); if ((rc = do_interact(T[i], sp, prof_of(i)))) return rc; ++T[i]->order_age; }
         const bool last = k + 1 == nsteps;
-        const bool resort_due = wants_morton(w, sp) && (w->order_age >= w->resort_every || w->next_order_pending);
+        const bool resort_due = wants_morton(w0, sp) && (w0->order_age >= w0->resort_every || w0->next_order_pending);
         const bool fuse = !sweep && !last && !resort_due;
-        if ((rc = do_integrate(w, sp, true, true, fuse, prof))) return rc;
-        if (sweep && (rc = do_sweep(w, w->player_ndx, prof))) return rc;
-        if (!fuse && !last && (rc = do_intrinsic_pack(w, sp, true, prof))) return rc;
+        for (size_t i = 0; i < T.size(); ++i) { USE(T[i]); if ((rc = do_integrate(T[i], sp, true, true, fuse, prof_of(i)))) return rc; }
+        if (sweep && (rc = team_sweep(T, w0->player_ndx, profs))) return rc;
+        if (!fuse && !last)
+            for (size_t i = 0; i < T.size(); ++i) { USE(T[i]); if ((rc = do_intrinsic_pack(T[i], sp, true, prof_of(i)))) return rc; }
     }
-    w->steps += nsteps;
+    for (oon_world* w : T) w->steps += nsteps;
     return OON_OK;
 }
 
@@ -850,8 +970,32 @@ int quiesce_aux(oon_world* w) {
     if (w->next_order_pending) CU(w, cudaStreamWaitEvent(w->stream, w->ev_sorted, 0));
     return OON_OK;
 }
+int team_quiesce(Team& T) {
+    for (oon_world* w : T) { USE(w); int rc = quiesce_aux(w); if (rc) return rc; }
+    return OON_OK;
+}
+int team_sync(Team& T) {
+    for (oon_world* w : T) { USE(w); SYNC(w); }
+    return OON_OK;
+}
 
 bool mortal(float lifetime) { return lifetime > 0.f || (lifetime != LIFETIME_UNLIMITED && lifetime <= 0.f); }
+
+// Which shard of the team (index into T, -1: none of mine) owns global body `ndx`, and where it sits there.
+// Needs fresh counts (team_sync_count).
+int owner_of(const oon_world* any, uint64_t ndx, uint32_t* local_out) {
+    uint64_t first = 0;
+    for (int g = 0; g < any->nranks; ++g) {
+        const uint32_t c = rank_count(any, g);
+        if (ndx < first + c) { *local_out = uint32_t(ndx - first); return g; }
+        first += c;
+    }
+    return -1;
+}
+oon_world* member_of_rank(Team& T, int rank) {
+    for (oon_world* w : T) if (w->rank == rank) return w;
+    return nullptr;
+}
 
 }  // namespace
 
@@ -865,6 +1009,7 @@ int oon_abi_version(void) { return OON_ABI_VERSION; }
 int oon_debug_time_interact(oon_world* w, float dt, uint32_t fraction, uint32_t part, float* ms) {
     CHECK_W(w);
     if (!ms) return fail(w, OON_ERR_INVALID, "null output");
+    if (!w->kids.empty()) return fail(w, OON_ERR_UNSUPPORTED, "oon_debug_time_interact works on a single-GPU handle");
     if (!w->tiles_fresh || !w->block) return fail(w, OON_ERR_INVALID, "oon_debug_time_interact: call oon_update_intrinsic first");
     const StepParams sp = step_params(w, dt);
     if (!sp.n2n || sp.exact) return fail(w, OON_ERR_UNSUPPORTED, "oon_debug_time_interact times the FAST all-pairs kernel only");
@@ -908,7 +1053,8 @@ int oon_nccl_unique_id(void* out_id) {
     return OON_OK;
 }
 
-static int create_common(int device, int rank, int nranks, const void* id, oon_world** out) {
+// parent != nullptr: a shard of a group (no NCCL communicator: the group's host thread does the collectives in-process)
+static int create_common(int device, int rank, int nranks, const void* id, oon_world* parent, oon_world** out) {
     if (!out || nranks < 1 || rank < 0 || rank >= nranks) return fail(nullptr, OON_ERR_INVALID, "bad arguments to oon_create");
     *out = nullptr;
     int count = 0;
@@ -924,6 +1070,7 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
 
     auto* w = new oon_world;
     w->device = device; w->rank = rank; w->nranks = nranks;
+    w->team.push_back(w);
     oon_props_default(&w->props);
     w->sm_count = prop.multiProcessorCount;
     if (const char* e = getenv("OON_GROUP_TILES")) { long v = atol(e); if (v > 0) w->group_tiles_override = uint32_t(v); }
@@ -948,11 +1095,13 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
         CUB_(cudaStreamCreateWithPriority(&w->aux, cudaStreamNonBlocking, hi));   // small kernels: let them cut in front
     }
     CUB_(cudaEventCreateWithFlags(&w->ev_main, cudaEventDisableTiming)); CUB_(cudaEventCreateWithFlags(&w->ev_sorted, cudaEventDisableTiming));
+    CUB_(cudaEventCreateWithFlags(&w->ev_grp, cudaEventDisableTiming)); CUB_(cudaEventCreateWithFlags(&w->ev_grp_done, cudaEventDisableTiming));
     CUB_(cudaMalloc(&w->d_n, sizeof(uint32_t))); CUB_(cudaMemset(w->d_n, 0, sizeof(uint32_t)));
     CUB_(cudaMalloc(&w->d_removed_count, sizeof(uint32_t))); CUB_(cudaMemset(w->d_removed_count, 0, sizeof(uint32_t)));
     CUB_(cudaMalloc(&w->counters, sizeof(unsigned long long) * C_COUNT));
     CUB_(cudaMemset(w->counters, 0, sizeof(unsigned long long) * C_COUNT));
     CUB_(cudaMalloc(&w->fx_scale, sizeof(int))); CUB_(cudaMemset(w->fx_scale, 0, sizeof(int)));
+    CUB_(cudaMalloc(&w->emit_rec, sizeof(EmitBase) * size_t(nranks))); CUB_(cudaMemset(w->emit_rec, 0, sizeof(EmitBase) * size_t(nranks)));
     {
         const uint32_t init[3] = {0u, 0x7f61b1e6u /* BOX_EMPTY */, 0u};
         static_assert(BOX_EMPTY == 3.0e38f, "rank_stats initialiser");
@@ -969,28 +1118,75 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
         w->counts.assign(size_t(nranks), 0u);
     }
 #undef CUB_
-    if (nranks > 1) {
+    if (nranks > 1 && !parent) {
         if (!id) { w->error = "sharded world needs an NCCL unique id"; return bail(OON_ERR_INVALID); }
         if (!g_nccl.load()) { w->error = g_nccl.error; return bail(OON_ERR_NCCL); }
         ncclUniqueId uid; std::memcpy(&uid, id, sizeof uid);
         ncclResult_t r = g_nccl.CommInitRank(&w->comm, nranks, uid, rank);
         if (r != ncclSuccess) { w->error = std::string("ncclCommInitRank failed: ") + g_nccl.GetErrorString(r); return bail(OON_ERR_NCCL); }
     }
+    w->parent = parent;
     *out = w;
     return OON_OK;
 }
 
-int oon_create(int device, oon_world** out) { return create_common(device, 0, 1, nullptr, out); }
+int oon_create(int device, oon_world** out) { return create_common(device, 0, 1, nullptr, nullptr, out); }
 int oon_create_sharded(int device, int rank, int nranks, const void* nccl_unique_id, oon_world** out) {
-    return create_common(device, rank, nranks, nccl_unique_id, out);
+    return create_common(device, rank, nranks, nccl_unique_id, nullptr, out);
+}
+
+// One world over `ndev` GPUs of this process, driven by the calling thread (the reference is one process with a single
+// mutator, main.cpp:88-91, World.cpp:196-198): the shards reach each other's exchange buffers through peer access.
+int oon_create_multi(const int* devices, int ndev, oon_world** out) {
+    if (!out || !devices || ndev < 1 || ndev > 8) return fail(nullptr, OON_ERR_INVALID, "oon_create_multi: 1 to 8 devices");
+    *out = nullptr;
+    if (ndev == 1) return oon_create(devices[0], out);
+    for (int i = 0; i < ndev; ++i)
+        for (int j = 0; j < i; ++j)
+            if (devices[i] == devices[j]) return fail(nullptr, OON_ERR_INVALID, "oon_create_multi: device %d listed twice", devices[i]);
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); return fail(nullptr, OON_ERR_NO_DEVICE, "no CUDA device visible; this library has no CPU path"); }
+    for (int i = 0; i < ndev; ++i)
+        if (devices[i] < 0 || devices[i] >= count) return fail(nullptr, OON_ERR_INVALID, "device %d out of range (have %d)", devices[i], count);
+    for (int i = 0; i < ndev; ++i) {
+        if (cudaSetDevice(devices[i]) != cudaSuccess) return fail(nullptr, OON_ERR_CUDA, "cudaSetDevice(%d) failed", devices[i]);
+        for (int j = 0; j < ndev; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) != cudaSuccess || !can)
+                return fail(nullptr, OON_ERR_UNSUPPORTED, "oon_create_multi: device %d cannot access device %d (the shards exchange their tiles through peer memory)", devices[i], devices[j]);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(nullptr, OON_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", devices[i], devices[j], cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    }
+    auto* g = new oon_world;
+    g->device = -1; g->rank = 0; g->nranks = ndev;
+    oon_props_default(&g->props);
+    for (int i = 0; i < ndev; ++i) {
+        oon_world* kid = nullptr;
+        const int rc = create_common(devices[i], i, ndev, nullptr, g, &kid);
+        if (rc) { const std::string msg = g_create_error; oon_destroy(g); g_create_error = msg; return rc; }
+        g->kids.push_back(kid);
+    }
+    g->team = g->kids;
+    *out = g;
+    return OON_OK;
 }
 
 int oon_destroy(oon_world* w) {
     if (!w) return OON_ERR_INVALID;
+    if (!w->kids.empty() || w->device < 0) {               // group handle: quiesce every shard, then free them one by one
+        for (oon_world* k : w->kids) { cudaSetDevice(k->device); if (k->stream) cudaStreamSynchronize(k->stream); if (k->aux) cudaStreamSynchronize(k->aux); }
+        for (oon_world* k : w->kids) { k->p2p = false; oon_destroy(k); }
+        delete w;
+        return OON_OK;
+    }
     cudaSetDevice(w->device);
     if (w->stream) cudaStreamSynchronize(w->stream);
     if (w->aux) { cudaStreamSynchronize(w->aux); cudaStreamDestroy(w->aux); }
-    if (w->p2p && w->sticky == OON_OK) {
+    if (w->p2p && w->sticky == OON_OK && !in_group(w)) {
         // Collective: no kernel of any rank still stores into a peer's buffer, and nobody frees a buffer a peer still maps.
         barrier(w);
         p2p_close_tiles(w);
@@ -999,13 +1195,15 @@ int oon_destroy(oon_world* w) {
     }
     if (w->ev_main) cudaEventDestroy(w->ev_main);
     if (w->ev_sorted) cudaEventDestroy(w->ev_sorted);
+    if (w->ev_grp) cudaEventDestroy(w->ev_grp);
+    if (w->ev_grp_done) cudaEventDestroy(w->ev_grp_done);
     cudaFree(w->inv_next);
     if (w->copy_stream) { cudaStreamSynchronize(w->copy_stream); cudaStreamDestroy(w->copy_stream); cudaEventDestroy(w->ev_render_ready); cudaEventDestroy(w->ev_render_done); }
     if (w->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(w->comm);
     soa_free(w->soa[0]); soa_free(w->soa[1]);
     cudaFree(w->tiles_buf[0]); cudaFree(w->tiles_buf[1]); cudaFree(w->acc); cudaFree(w->touch); cudaFree(w->fx_scale); cudaFree(w->rank_stats);
     cudaFree(w->flags); if (w->timeouts_host) cudaFreeHost(w->timeouts_host); cudaFree(w->ipc_stage); cudaFree(w->runinfo); cudaFree(w->d_counts); cudaFree(w->partial); cudaFree(w->scratch4); cudaFree(w->kick); cudaFree(w->d_n); cudaFree(w->d_removed_count);
-    cudaFree(w->counters); cudaFree(w->sweep_temp); cudaFree(w->sweep_scratch); cudaFree(w->removed_idx); cudaFree(w->aos_dev);
+    cudaFree(w->counters); cudaFree(w->sweep_temp); cudaFree(w->sweep_scratch); cudaFree(w->removed_idx); cudaFree(w->aos_dev); cudaFree(w->emit_rec);
     cudaFree(w->xyr_dev); cudaFree(w->cap.coll); cudaFree(w->cap.touch);
     cudaFree(w->inv); cudaFree(w->order_temp); cudaFree(w->order_keys); cudaFree(w->order_vals); cudaFree(w->order_bounds);
     if (w->ev_start) cudaEventDestroy(w->ev_start);
@@ -1018,6 +1216,12 @@ int oon_destroy(oon_world* w) {
     return OON_OK;
 }
 
+int oon_device_count(const oon_world* w, int* n_out) {
+    if (!w || !n_out) return OON_ERR_INVALID;
+    *n_out = int(w->team.size());
+    return OON_OK;
+}
+
 int oon_set_props(oon_world* w, const oon_props* p) {
     CHECK_W(w);
     if (!p) return fail(w, OON_ERR_INVALID, "null props");
@@ -1025,6 +1229,7 @@ int oon_set_props(oon_world* w, const oon_props* p) {
     if (p->collision_mode > OON_COLLISION_GLIDE_THROUGH) return fail(w, OON_ERR_INVALID, "collision_mode %u out of range", p->collision_mode);
     if (p->loop_mode > OON_LOOP_FULL_MATRIX) return fail(w, OON_ERR_INVALID, "loop_mode %u out of range", p->loop_mode);
     w->props = *p;
+    for (oon_world* m : w->team) m->props = *p;
     return OON_OK;
 }
 int oon_get_props(const oon_world* w, oon_props* out) {
@@ -1036,6 +1241,7 @@ int oon_set_math_mode(oon_world* w, int mode) {
     CHECK_W(w);
     if (mode != OON_MATH_FAST && mode != OON_MATH_EXACT) return fail(w, OON_ERR_INVALID, "math mode %d out of range", mode);
     w->math_mode = mode;
+    for (oon_world* m : w->team) m->math_mode = mode;
     return OON_OK;
 }
 int oon_get_math_mode(const oon_world* w, int* mode) {
@@ -1043,76 +1249,85 @@ int oon_get_math_mode(const oon_world* w, int* mode) {
     *mode = w->math_mode;
     return OON_OK;
 }
+int oon_set_player_index(oon_world* w, uint64_t ndx) {
+    CHECK_W(w);
+    if (ndx > 0x3fffffffull) return fail(w, OON_ERR_INVALID, "player index %llu out of range", (unsigned long long)ndx);
+    w->player_ndx = uint32_t(ndx);
+    for (oon_world* m : w->team) m->player_ndx = uint32_t(ndx);
+    return OON_OK;
+}
 
-// Replace the world by n bodies.  `src` = the whole table in host order (is_block == false) or this rank's block of it
-// (is_block == true, `count` bodies starting at global index rank * block).  Only the rank's own block crosses the bus.
-// Whether any body can expire (then the frames include the sweep) is found by the unpack kernel, one flag per rank; a
-// sharded world agrees on it with a one-word all-gather — round 1 walked the whole 60-byte-per-body host table on every
-// rank for this, which cost more than the PCIe copy of the block.
-static int upload_common(oon_world* w, const oon_body_f32* src, bool is_block, uint64_t count, uint64_t n) {
-    { int qrc = quiesce_aux(w); if (qrc) return qrc; }
-    if (n && !src && !(is_block && !count)) return fail(w, OON_ERR_INVALID, "null body table");
-    int rc = layout(w, n, 0);
+// Replace the world by n bodies (with room for n_cap >= n).  `src` = the whole table in host order (is_block == false) or,
+// for one rank of a multi-process world, its block of it (is_block == true, `count` bodies starting at global index
+// rank * block).  Only a shard's own block crosses the bus.  Whether any body can expire (then the frames include the sweep)
+// is found by the unpack kernels, one flag per shard; the ranks of a multi-process world agree on it with a one-word
+// all-gather — round 1 walked the whole 60-byte-per-body host table on every rank for this, which cost more than the PCIe
+// copy of the block.
+static int upload_common(oon_world* h, const oon_body_f32* src, bool is_block, uint64_t count, uint64_t n, uint64_t n_cap) {
+    Team& T = h->team;
+    int rc = team_quiesce(T);
     if (rc) return rc;
-    const uint64_t lo = uint64_t(w->rank) * w->block;
-    if (is_block && count != w->n_local)
-        return fail(w, OON_ERR_INVALID, "upload_local: rank %d of %d owns %u bodies of a %llu-body world (from index %llu), got %llu",
-                    w->rank, w->nranks, w->n_local, (unsigned long long)n, (unsigned long long)lo, (unsigned long long)count);
-    const oon_body_f32* mine = is_block ? src : src + lo;
-    CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));     // doubles as the unpack kernel's "mortal seen" flag
-    if (w->n_local) {
-        if ((rc = ensure_aos(w, w->n_local))) return rc;
-        CU(w, cudaMemcpyAsync(w->aos_dev, mine, size_t(w->n_local) * sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
-        w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, 0, w->n_local, w->d_removed_count);
-        CU(w, cudaGetLastError());
+    if (n && !src && !(is_block && !count)) return fail(h, OON_ERR_INVALID, "null body table");
+    if (is_block && T.size() > 1) return fail(h, OON_ERR_INVALID, "upload_local on a group handle: the group takes the whole table (oon_upload)");
+    if ((rc = team_layout(T, std::max(n, n_cap), n, false))) return rc;
+    for (oon_world* w : T) {
+        USE(w);
+        const uint64_t lo = uint64_t(w->rank) * w->block;
+        if (is_block && count != w->n_local)
+            return fail(w, OON_ERR_INVALID, "upload_local: rank %d of %d owns %u bodies of a %llu-body world (from index %llu), got %llu",
+                        w->rank, w->nranks, w->n_local, (unsigned long long)n, (unsigned long long)lo, (unsigned long long)count);
+        const oon_body_f32* mine = is_block ? src : src + lo;
+        CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));     // doubles as the unpack kernel's "mortal seen" flag
+        if (w->n_local) {
+            if ((rc = ensure_aos(w, w->n_local))) return rc;
+            CU(w, cudaMemcpyAsync(w->aos_dev, mine, size_t(w->n_local) * sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
+            w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, 0, w->n_local, w->d_removed_count);
+            CU(w, cudaGetLastError());
+        }
+        CU(w, cudaMemcpyAsync(w->d_n, &w->n_local, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
     }
-    CU(w, cudaMemcpyAsync(w->d_n, &w->n_local, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
-    std::vector<uint32_t> seen(size_t(w->nranks), 0u);
-    if (w->nranks > 1) {
-        CU(w, cudaMemcpyAsync(w->d_counts + w->rank, w->d_removed_count, sizeof(uint32_t), cudaMemcpyDeviceToDevice, w->stream));
-        NC(w, g_nccl.AllGather(w->d_counts + w->rank, w->d_counts, 1, ncclUint32, w->comm, w->stream));
-        CU(w, cudaMemcpyAsync(seen.data(), w->d_counts, sizeof(uint32_t) * seen.size(), cudaMemcpyDeviceToHost, w->stream));
-    } else {
-        CU(w, cudaMemcpyAsync(seen.data(), w->d_removed_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+    std::vector<uint32_t> seen(size_t(T[0]->nranks), 0u);
+    for (oon_world* w : T) {
+        USE(w);
+        if (T.size() == 1 && w->nranks > 1) {
+            CU(w, cudaMemcpyAsync(w->d_counts + w->rank, w->d_removed_count, sizeof(uint32_t), cudaMemcpyDeviceToDevice, w->stream));
+            NC(w, g_nccl.AllGather(w->d_counts + w->rank, w->d_counts, 1, ncclUint32, w->comm, w->stream));
+            CU(w, cudaMemcpyAsync(seen.data(), w->d_counts, sizeof(uint32_t) * seen.size(), cudaMemcpyDeviceToHost, w->stream));
+        } else {
+            CU(w, cudaMemcpyAsync(&seen[size_t(w->rank)], w->d_removed_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+        }
+        CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));
     }
-    CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));
-    SYNC(w);                                         // the caller may reuse the host table immediately (pageable memory)
+    if ((rc = team_sync(T))) return rc;                    // the caller may reuse the host table immediately (pageable memory)
     uint32_t any = 0;
     for (uint32_t v : seen) any |= v;
-    w->has_mortals = any != 0;
-    for (int g = 0; g < w->nranks && !w->counts.empty(); ++g) {          // the even split, until a sweep makes the blocks ragged
-        const uint64_t glo = uint64_t(g) * w->block;
-        w->counts[size_t(g)] = n > glo ? uint32_t(std::min<uint64_t>(w->block, n - glo)) : 0u;
-    }
+    for (oon_world* w : T) w->has_mortals = any != 0;
     return OON_OK;
 }
 
 int oon_upload(oon_world* w, const oon_body_f32* bodies, uint64_t n) {
     CHECK_W(w);
-    return upload_common(w, bodies, false, 0, n);
+    return upload_common(w, bodies, false, 0, n, n);
 }
 
 int oon_upload_local(oon_world* w, const oon_body_f32* block, uint64_t count, uint64_t n_total) {
     CHECK_W(w);
-    return upload_common(w, block, true, count, n_total);
+    if (!w->kids.empty()) {                                // a group is one "rank" to its caller: its block is the whole table
+        if (count != n_total) return fail(w, OON_ERR_INVALID, "upload_local on a group handle: the group owns the whole table (%llu bodies), got %llu", (unsigned long long)n_total, (unsigned long long)count);
+        return upload_common(w, block, false, 0, n_total, n_total);
+    }
+    return upload_common(w, block, true, count, n_total, n_total);
 }
 
 int oon_shard_range(uint64_t n_total, int rank, int nranks, uint64_t* first_out, uint64_t* count_out) {
     if (nranks < 1 || rank < 0 || rank >= nranks) return OON_ERR_INVALID;
-    const bool canon = (nranks == 1 || nranks == 2 || nranks == 4 || nranks == 8);      // == layout()
+    const bool canon = (nranks == 1 || nranks == 2 || nranks == 4 || nranks == 8);      // == layout_one()
     const uint32_t nblocks = canon ? 8u : uint32_t(nranks);
     const uint64_t cblock = std::max<uint64_t>(TS, (((n_total + nblocks - 1) / nblocks) + TS - 1) / TS * TS);
     const uint64_t block = cblock * (nblocks / uint32_t(nranks));
     const uint64_t lo = std::min<uint64_t>(n_total, uint64_t(rank) * block);
     if (first_out) *first_out = lo;
     if (count_out) *count_out = std::min<uint64_t>(block, n_total - lo);
-    return OON_OK;
-}
-
-int oon_set_player_index(oon_world* w, uint64_t ndx) {
-    CHECK_W(w);
-    if (ndx > 0x3fffffffull) return fail(w, OON_ERR_INVALID, "player index %llu out of range", (unsigned long long)ndx);
-    w->player_ndx = uint32_t(ndx);
     return OON_OK;
 }
 
@@ -1132,54 +1347,62 @@ int oon_upload_f64(oon_world* w, const oon_body_f64* bodies, uint64_t n) {
     return oon_upload(w, tmp.data(), n);
 }
 
-// Gather the whole world into aos_dev (device), in host order.  Sharded: all-gather of the packed blocks.
-static int gather_aos(oon_world* w, uint64_t* n_out) {
-    int rc = sync_count(w);
+// The whole world in host order.  One GPU / group: every shard packs its own block and copies it straight to its place in the
+// caller's table (a group's shards copy in parallel, one PCIe link each).  One rank of a multi-process world: all-gather of
+// the packed blocks, then the whole table (every rank gets everything; use oon_download_local for the rank's own block).
+static int download_common(oon_world* h, oon_body_f32* out, uint64_t capacity, uint64_t* n_out) {
+    Team& T = h->team;
+    int rc = team_sync_count(T);
     if (rc) return rc;
-    const uint64_t n = w->n_total;
-    if (w->nranks == 1) {
-        if ((rc = ensure_aos(w, n))) return rc;
-        w->launches += launch_pack_f32(w->stream, w->soa[w->cur].d, w->aos_dev, 0, uint32_t(n));
-        CU(w, cudaGetLastError());
-    } else {
+    oon_world* w0 = T[0];
+    const uint64_t n = w0->n_total;
+    if (n_out) *n_out = n;
+    if (n > capacity) return fail(h, OON_ERR_CAPACITY, "download needs room for %llu bodies, got %llu", (unsigned long long)n, (unsigned long long)capacity);
+    if (n && !out) return fail(h, OON_ERR_INVALID, "null output");
+    if (T.size() == 1 && w0->nranks > 1) {
+        oon_world* w = w0;
         const size_t per = size_t(w->block);
         if ((rc = ensure_aos(w, per * w->nranks))) return rc;
         w->launches += launch_pack_f32(w->stream, w->soa[w->cur].d, w->aos_dev + per * w->rank, 0, w->n_local);
         CU(w, cudaGetLastError());
         NC(w, g_nccl.AllGather(w->aos_dev + per * w->rank, w->aos_dev, per * sizeof(oon_body_f32), ncclChar, w->comm, w->stream));
+        uint64_t at = 0;
+        for (int g = 0; g < w->nranks; ++g) {               // one copy per rank: after a sweep the blocks hold fewer bodies than slots
+            const uint32_t c = rank_count(w, g);
+            if (c) CU(w, cudaMemcpyAsync(out + at, w->aos_dev + size_t(g) * w->block, size_t(c) * sizeof(oon_body_f32), cudaMemcpyDeviceToHost, w->stream));
+            at += c;
+        }
+        SYNC(w);
+        return OON_OK;
     }
-    *n_out = n;
-    return OON_OK;
+    for (oon_world* w : T) {
+        USE(w);
+        if (!w->n_local) continue;
+        if ((rc = ensure_aos(w, w->n_local))) return rc;
+        w->launches += launch_pack_f32(w->stream, w->soa[w->cur].d, w->aos_dev, 0, w->n_local);
+        CU(w, cudaGetLastError());
+        CU(w, cudaMemcpyAsync(out + rank_first(w, w->rank), w->aos_dev, size_t(w->n_local) * sizeof(oon_body_f32), cudaMemcpyDeviceToHost, w->stream));
+    }
+    return team_sync(T);
 }
 
 int oon_download(oon_world* w, oon_body_f32* out, uint64_t capacity, uint64_t* n_out) {
     CHECK_W(w);
-    uint64_t n = 0;
-    int rc = gather_aos(w, &n);
-    if (rc) return rc;
-    if (n_out) *n_out = n;
-    if (n > capacity) return fail(w, OON_ERR_CAPACITY, "download needs room for %llu bodies, got %llu", (unsigned long long)n, (unsigned long long)capacity);
-    if (n && !out) return fail(w, OON_ERR_INVALID, "null output");
-    // one copy per rank: after a sweep the ranks' blocks hold fewer bodies than slots
-    uint64_t at = 0;
-    for (int g = 0; g < w->nranks; ++g) {
-        const uint32_t c = w->nranks == 1 ? uint32_t(n) : rank_count(w, g);
-        if (c) CU(w, cudaMemcpyAsync(out + at, w->aos_dev + size_t(g) * w->block, size_t(c) * sizeof(oon_body_f32), cudaMemcpyDeviceToHost, w->stream));
-        at += c;
-    }
-    SYNC(w);
-    return OON_OK;
+    return download_common(w, out, capacity, n_out);
 }
 
 // Shard-local read-back: the bodies this rank owns, nothing else — no collective on the data path, one D2H copy of the
 // rank's own block (a full oon_download on 8 ranks all-gathers 60 B/body and then copies the whole table on EVERY rank).
 int oon_download_local(oon_world* w, oon_body_f32* block_out, uint64_t capacity, uint64_t* first_out, uint64_t* n_out) {
     CHECK_W(w);
-    int rc = sync_count(w);                                  // only worlds whose bodies can expire pay for the count exchange
+    if (!w->kids.empty()) {                                // a group owns the whole table
+        if (first_out) *first_out = 0;
+        return download_common(w, block_out, capacity, n_out);
+    }
+    int rc = team_sync_count(w->team);                       // only worlds whose bodies can expire pay for the count exchange
     if (rc) return rc;
-    uint64_t first = 0;
-    for (int g = 0; g < w->rank; ++g) first += rank_count(w, g);
-    const uint64_t n = w->nranks == 1 ? w->n_total : w->n_local;
+    const uint64_t first = rank_first(w, w->rank);
+    const uint64_t n = w->n_local;
     if (first_out) *first_out = first;
     if (n_out) *n_out = n;
     if (n > capacity) return fail(w, OON_ERR_CAPACITY, "local download needs room for %llu bodies, got %llu", (unsigned long long)n, (unsigned long long)capacity);
@@ -1196,9 +1419,11 @@ int oon_download_local(oon_world* w, oon_body_f32* block_out, uint64_t capacity,
 
 int oon_download_f64(oon_world* w, oon_body_f64* out, uint64_t capacity, uint64_t* n_out) {
     CHECK_W(w);
-    std::vector<oon_body_f32> tmp(w->n_total);
+    int rc = team_sync_count(w->team);
+    if (rc) return rc;
+    std::vector<oon_body_f32> tmp(w->team[0]->n_total);
     uint64_t n = 0;
-    int rc = oon_download(w, tmp.data(), tmp.size(), &n);
+    rc = oon_download(w, tmp.data(), tmp.size(), &n);
     if (n_out) *n_out = n;
     if (rc) return rc;
     if (n > capacity) return fail(w, OON_ERR_CAPACITY, "download needs room for %llu bodies", (unsigned long long)n);
@@ -1213,95 +1438,183 @@ int oon_download_f64(oon_world* w, oon_body_f64* out, uint64_t capacity, uint64_
     return OON_OK;
 }
 
-// Pack {x, y, r} of every body on the main stream (sharded: gather the ranks' blocks) and copy them to the host on the
-// copy stream; the main stream is free for the next frames as soon as the pack is enqueued.
-static int render_enqueue(oon_world* w, float* xyr, uint64_t capacity, uint64_t* n_out) {
-    int rc = sync_count(w);
+// Pack the render read set {x, y, r, colour} of every body on the shards' main streams and copy it to the host on their copy
+// streams; the main streams are free for the next frames as soon as the packs are enqueued.  One rank of a multi-process
+// world gathers the ranks' blocks first (every rank gets everything).
+static int render_enqueue(oon_world* h, float* xyr, uint32_t* colors, uint64_t capacity, uint64_t* n_out) {
+    Team& T = h->team;
+    int rc = team_sync_count(T);
     if (rc) return rc;
-    const uint64_t n = w->n_total;
+    const uint64_t n = T[0]->n_total;
     if (n_out) *n_out = n;
-    if (n > capacity) return fail(w, OON_ERR_CAPACITY, "render download needs room for %llu bodies", (unsigned long long)n);
-    if (n && !xyr) return fail(w, OON_ERR_INVALID, "null output");
-    if (!w->copy_stream) {
-        CU(w, cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
-        CU(w, cudaEventCreateWithFlags(&w->ev_render_ready, cudaEventDisableTiming));
-        CU(w, cudaEventCreateWithFlags(&w->ev_render_done, cudaEventDisableTiming));
+    if (n > capacity) return fail(h, OON_ERR_CAPACITY, "render download needs room for %llu bodies", (unsigned long long)n);
+    if (n && !xyr) return fail(h, OON_ERR_INVALID, "null output");
+    for (oon_world* w : T) {
+        USE(w);
+        if (!w->copy_stream) {
+            CU(w, cudaStreamCreateWithFlags(&w->copy_stream, cudaStreamNonBlocking));
+            CU(w, cudaEventCreateWithFlags(&w->ev_render_ready, cudaEventDisableTiming));
+            CU(w, cudaEventCreateWithFlags(&w->ev_render_done, cudaEventDisableTiming));
+        }
+        if (w->render_pending) CU(w, cudaStreamWaitEvent(w->stream, w->ev_render_done, 0));   // the staging buffer is still being read
+        const bool gather = T.size() == 1 && w->nranks > 1;
+        const size_t per = size_t(w->block) * 4;             // 3 floats + the colour word per slot
+        const size_t need = gather ? per * w->nranks : per;
+        if (need > w->xyr_cap) {
+            if (w->render_pending) CU(w, cudaEventSynchronize(w->ev_render_done));
+            cudaFree(w->xyr_dev); w->xyr_dev = nullptr; w->xyr_cap = 0;
+            if ((rc = dev_alloc(w, &w->xyr_dev, need + need / 2))) return rc;
+            w->xyr_cap = need + need / 2;
+        }
+        float* mine = w->xyr_dev + (gather ? per * w->rank : 0);
+        w->launches += launch_render_pack(w->stream, w->soa[w->cur].d, w->d_n, w->block, mine, reinterpret_cast<uint32_t*>(mine + size_t(w->block) * 3));
+        CU(w, cudaGetLastError());
+        if (gather) NC(w, g_nccl.AllGather(mine, w->xyr_dev, per, ncclFloat, w->comm, w->stream));
+        CU(w, cudaEventRecord(w->ev_render_ready, w->stream));
+        CU(w, cudaStreamWaitEvent(w->copy_stream, w->ev_render_ready, 0));
+        if (gather) {
+            uint64_t at = 0;
+            for (int g = 0; g < w->nranks; ++g) {              // one copy per rank (ragged blocks after a sweep)
+                const uint32_t c = rank_count(w, g);
+                const float* src = w->xyr_dev + per * size_t(g);
+                if (c) CU(w, cudaMemcpyAsync(xyr + at * 3, src, size_t(c) * 3 * sizeof(float), cudaMemcpyDeviceToHost, w->copy_stream));
+                if (c && colors) CU(w, cudaMemcpyAsync(colors + at, src + size_t(w->block) * 3, size_t(c) * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->copy_stream));
+                at += c;
+            }
+        } else if (w->n_local) {
+            const uint64_t at = rank_first(w, w->rank);
+            CU(w, cudaMemcpyAsync(xyr + at * 3, mine, size_t(w->n_local) * 3 * sizeof(float), cudaMemcpyDeviceToHost, w->copy_stream));
+            if (colors) CU(w, cudaMemcpyAsync(colors + at, mine + size_t(w->block) * 3, size_t(w->n_local) * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->copy_stream));
+        }
+        CU(w, cudaEventRecord(w->ev_render_done, w->copy_stream));
+        w->render_pending = true;
+        w->render_count = n;
     }
-    if (w->render_pending) CU(w, cudaStreamWaitEvent(w->stream, w->ev_render_done, 0));   // the staging buffer is still being read
-    const size_t per = size_t(w->block) * 3;
-    const size_t need = per * w->nranks;
-    if (need > w->xyr_cap) {
-        if (w->render_pending) CU(w, cudaEventSynchronize(w->ev_render_done));
-        cudaFree(w->xyr_dev); w->xyr_dev = nullptr; w->xyr_cap = 0;
-        if ((rc = dev_alloc(w, &w->xyr_dev, need + need / 2))) return rc;
-        w->xyr_cap = need + need / 2;
+    h->render_pending = true;
+    h->render_count = n;
+    return OON_OK;
+}
+
+static int render_wait(oon_world* h, uint64_t* n_out) {
+    for (oon_world* w : h->team) {
+        USE(w);
+        CU(w, cudaEventSynchronize(w->ev_render_done));
+        w->render_pending = false;
+        int rc = peers_ok(w);
+        if (rc) return rc;
     }
-    w->launches += launch_render_pack(w->stream, w->soa[w->cur].d, w->d_n, w->block, w->xyr_dev + per * w->rank);
-    CU(w, cudaGetLastError());
-    if (w->nranks > 1) NC(w, g_nccl.AllGather(w->xyr_dev + per * w->rank, w->xyr_dev, per, ncclFloat, w->comm, w->stream));
-    CU(w, cudaEventRecord(w->ev_render_ready, w->stream));
-    CU(w, cudaStreamWaitEvent(w->copy_stream, w->ev_render_ready, 0));
-    uint64_t at = 0;
-    for (int g = 0; g < w->nranks; ++g) {                  // one copy per rank (ragged blocks after a sweep)
-        const uint32_t c = w->nranks == 1 ? uint32_t(n) : rank_count(w, g);
-        if (c) CU(w, cudaMemcpyAsync(xyr + at * 3, w->xyr_dev + per * size_t(g), size_t(c) * 3 * sizeof(float), cudaMemcpyDeviceToHost, w->copy_stream));
-        at += c;
-    }
-    CU(w, cudaEventRecord(w->ev_render_done, w->copy_stream));
-    w->render_pending = true;
-    w->render_count = n;
+    h->render_pending = false;
+    if (n_out) *n_out = h->render_count;
     return OON_OK;
 }
 
 int oon_download_render(oon_world* w, float* xyr, uint64_t capacity, uint64_t* n_out) {
     CHECK_W(w);
-    int rc = render_enqueue(w, xyr, capacity, n_out);
+    int rc = render_enqueue(w, xyr, nullptr, capacity, n_out);
     if (rc) return rc;
-    CU(w, cudaEventSynchronize(w->ev_render_done));
-    w->render_pending = false;
-    return peers_ok(w);
+    return render_wait(w, nullptr);
+}
+
+int oon_download_render_rgb(oon_world* w, float* xyr, uint32_t* colors, uint64_t capacity, uint64_t* n_out) {
+    CHECK_W(w);
+    if (!colors) return fail(w, OON_ERR_INVALID, "null colour output");
+    int rc = render_enqueue(w, xyr, colors, capacity, n_out);
+    if (rc) return rc;
+    return render_wait(w, nullptr);
 }
 
 int oon_download_render_begin(oon_world* w, float* xyr_pinned, uint64_t capacity) {
     CHECK_W(w);
-    return render_enqueue(w, xyr_pinned, capacity, nullptr);
+    return render_enqueue(w, xyr_pinned, nullptr, capacity, nullptr);
 }
 
 int oon_download_render_end(oon_world* w, uint64_t* n_out) {
     CHECK_W(w);
     if (!w->render_pending) return fail(w, OON_ERR_INVALID, "oon_download_render_end without oon_download_render_begin");
-    CU(w, cudaEventSynchronize(w->ev_render_done));
-    w->render_pending = false;
-    if (n_out) *n_out = w->render_count;
-    return peers_ok(w);
+    return render_wait(w, n_out);
 }
 
 int oon_body_count(oon_world* w, uint64_t* n_out) {
     CHECK_W(w);
     if (!n_out) return fail(w, OON_ERR_INVALID, "null output");
-    int rc = sync_count(w);
+    int rc = team_sync_count(w->team);
     if (rc) return rc;
-    *n_out = w->n_total;
+    *n_out = w->team[0]->n_total;
     return OON_OK;
 }
 
-int oon_add_bodies(oon_world* w, const oon_body_f32* bodies, uint64_t k) {
-    CHECK_W(w);
-    { int qrc = quiesce_aux(w); if (qrc) return qrc; }
-    if (!k) return OON_OK;
-    if (!bodies) return fail(w, OON_ERR_INVALID, "null body table");
-    if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "add_bodies on a sharded world: re-upload the table instead");
-    int rc = sync_count(w);
+// ---- edits of the body table ------------------------------------------------------------------------------------------
+// Sharded worlds (multi-process: every rank makes the same call with the same arguments; group: one call) route an edit to
+// the shard that owns the body; the bookkeeping (counts, totals, "bodies can expire") is updated identically everywhere
+// without communication.  Appends go to the tail of the table: the last non-empty rank, or the next one when that is full.
+
+// Make room for k more bodies at the tail; *append_rank_out = rank that takes them.  When neither the last non-empty rank
+// nor its successor has the room, the whole world is laid out afresh for the larger size (through the host: rare).
+static int make_room(oon_world* h, uint64_t k, int* append_rank_out) {
+    Team& T = h->team;
+    int rc = team_sync_count(T);
     if (rc) return rc;
-    const uint32_t old_n = w->n_local;
-    if ((rc = layout(w, uint64_t(old_n) + k, old_n))) return rc;
-    if ((rc = ensure_aos(w, k))) return rc;
-    for (uint64_t i = 0; i < k; ++i) w->has_mortals |= mortal(bodies[i].lifetime);
-    CU(w, cudaMemcpyAsync(w->aos_dev, bodies, size_t(k) * sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
-    w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, old_n, uint32_t(k), nullptr);
-    CU(w, cudaGetLastError());
-    CU(w, cudaMemcpyAsync(w->d_n, &w->n_local, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
-    SYNC(w);
+    oon_world* w0 = T[0];
+    if (w0->nranks == 1) {
+        if (uint64_t(w0->n_local) + k > w0->block) {
+            const uint32_t keep = w0->n_local;
+            if ((rc = team_layout(T, uint64_t(keep) + k, keep, true))) return rc;
+        }
+        *append_rank_out = 0;
+        return OON_OK;
+    }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        int last = 0;
+        for (int g = 0; g < w0->nranks; ++g) if (rank_count(w0, g)) last = g;
+        if (uint64_t(rank_count(w0, last)) + k <= w0->block) { *append_rank_out = last; return OON_OK; }
+        if (last + 1 < w0->nranks && k <= w0->block) { *append_rank_out = last + 1; return OON_OK; }
+        if (attempt) break;
+        // no room at the tail: gather the table on the host and lay the world out again with room for k more
+        const uint64_t n = w0->n_total;
+        std::vector<oon_body_f32> all(n);
+        uint64_t got = 0;
+        if ((rc = download_common(h, all.data(), n, &got))) return rc;
+        const bool mortals = w0->has_mortals;
+        if ((rc = upload_common(h, all.data(), false, 0, n, n + k))) return rc;
+        for (oon_world* w : T) w->has_mortals = w->has_mortals || mortals;
+    }
+    return fail(h, OON_ERR_CAPACITY, "cannot append %llu bodies to the sharded world", (unsigned long long)k);
+}
+
+static void note_append(Team& T, int rank, uint64_t k, bool mortals) {
+    for (oon_world* w : T) {
+        if (w->nranks > 1) w->counts[size_t(rank)] += uint32_t(k);
+        if (w->rank == rank) w->n_local += uint32_t(k);
+        w->n_total += k;
+        w->has_mortals = w->has_mortals || mortals;
+        w->tiles_fresh = false;
+        w->order_dirty = true;                             // the slot order does not know the new bodies
+        w->kick_valid = false;
+    }
+}
+
+int oon_add_bodies(oon_world* h, const oon_body_f32* bodies, uint64_t k) {
+    CHECK_W(h);
+    Team& T = h->team;
+    int rc = team_quiesce(T);
+    if (rc) return rc;
+    if (!k) return OON_OK;
+    if (!bodies) return fail(h, OON_ERR_INVALID, "null body table");
+    int arank = 0;
+    if ((rc = make_room(h, k, &arank))) return rc;
+    bool mortals = false;
+    for (uint64_t i = 0; i < k; ++i) mortals |= mortal(bodies[i].lifetime);
+    if (oon_world* w = member_of_rank(T, arank)) {
+        USE(w);
+        if ((rc = ensure_aos(w, k))) return rc;
+        const uint32_t at = w->n_local, now = w->n_local + uint32_t(k);
+        CU(w, cudaMemcpyAsync(w->aos_dev, bodies, size_t(k) * sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
+        w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, at, uint32_t(k), nullptr);
+        CU(w, cudaGetLastError());
+        CU(w, cudaMemcpyAsync(w->d_n, &now, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+        SYNC(w);
+    }
+    note_append(T, arank, k, mortals);
     return OON_OK;
 }
 
@@ -1319,37 +1632,63 @@ int oon_emitter_cfg_default(oon_emitter_cfg* out) {
     return OON_OK;
 }
 
-// The reference's three body-creating loops share one device kernel (k_emit) and this host side.
-static int emit_common(oon_world* w, int kind, uint64_t base_ndx, uint64_t parent_ndx, uint32_t n, const oon_emitter_cfg* cfg,
+// The reference's three body-creating loops share one device kernel (k_emit) and this host side.  The emitter, the parent
+// and the tail of the table may live on three different shards: the owners publish the fields the loop reads as EmitBase
+// records, one small all-gather brings them to the append rank, a second one takes the result (particles appended, the
+// emitter's depleted mass and recalculated radius) back.
+static int emit_common(oon_world* h, int kind, uint64_t base_ndx, uint64_t parent_ndx, uint32_t n, const oon_emitter_cfg* cfg,
                        const float* nozzles_xy, uint64_t seed, uint32_t* emitted_out, const char* what) {
-    { int qrc = quiesce_aux(w); if (qrc) return qrc; }
-    if (emitted_out) *emitted_out = 0;
-    if (!cfg) return fail(w, OON_ERR_INVALID, "%s: null configuration", what);
-    if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "%s on a sharded world is not implemented in this build", what);
-    int rc = sync_count(w);
+    Team& T = h->team;
+    int rc = team_quiesce(T);
     if (rc) return rc;
-    if (base_ndx >= w->n_local || parent_ndx >= w->n_local)
-        return fail(w, OON_ERR_INVALID, "%s: body index %llu out of range (%u bodies)", what, (unsigned long long)std::max(base_ndx, parent_ndx), w->n_local);
+    if (emitted_out) *emitted_out = 0;
+    if (!cfg) return fail(h, OON_ERR_INVALID, "%s: null configuration", what);
+    if ((rc = team_sync_count(T))) return rc;
+    oon_world* w0 = T[0];
+    if (base_ndx >= w0->n_total || parent_ndx >= w0->n_total)
+        return fail(h, OON_ERR_INVALID, "%s: body index %llu out of range (%llu bodies)", what, (unsigned long long)std::max(base_ndx, parent_ndx), (unsigned long long)w0->n_total);
     if (!n) return OON_OK;
-    const uint32_t old_n = w->n_local;
-    if ((rc = layout(w, uint64_t(old_n) + n, old_n))) return rc;        // room for all n; the count is corrected below
-    float2* nozzles_dev = nullptr;
-    if (nozzles_xy) {
-        if ((rc = ensure_aos(w, (size_t(n) * sizeof(float2) + sizeof(oon_body_f32) - 1) / sizeof(oon_body_f32)))) return rc;
-        nozzles_dev = reinterpret_cast<float2*>(w->aos_dev);
-        CU(w, cudaMemcpyAsync(nozzles_dev, nozzles_xy, size_t(n) * sizeof(float2), cudaMemcpyHostToDevice, w->stream));
+    int arank = 0;
+    if ((rc = make_room(h, n, &arank))) return rc;         // room for all n; the counts are corrected below
+    uint32_t elocal = 0, plocal = 0;
+    const int erank = owner_of(w0, base_ndx, &elocal), prank = owner_of(w0, parent_ndx, &plocal);
+    const bool sharded = w0->nranks > 1;
+    auto rec_of = [](oon_world* m) { return reinterpret_cast<char*>(m->emit_rec); };
+    if (sharded && T.size() > 1 && (rc = group_before_produce(T))) return rc;
+    for (oon_world* w : T) {
+        USE(w);
+        const int e = w->rank == erank ? int(elocal) : -1, p = w->rank == prank ? int(plocal) : -1;
+        if (e >= 0 || p >= 0) { w->launches += uint64_t(launch_emit_fetch(w->stream, w->soa[w->cur].d, e, p, w->emit_rec + w->rank)); CU(w, cudaGetLastError()); }
     }
-    CU(w, cudaMemcpyAsync(w->d_n, &old_n, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
-    w->launches += uint64_t(launch_emit(w->stream, w->soa[w->cur].d, w->d_n, uint32_t(base_ndx), uint32_t(parent_ndx), n, *cfg, nozzles_dev, seed, kind,
-                                        w->d_removed_count));
-    CU(w, cudaGetLastError());
-    uint32_t emitted = 0;
-    CU(w, cudaMemcpyAsync(&emitted, w->d_removed_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
-    CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));
-    SYNC(w);
-    if ((rc = layout(w, uint64_t(old_n) + emitted, old_n + emitted))) return rc;   // bookkeeping only: capacity is there
-    if (emitted && kind != EMIT_SPAWN) w->has_mortals |= mortal(cfg->particle_lifetime);
-    if (emitted_out) *emitted_out = emitted;
+    if (sharded && (rc = team_allgather(T, rec_of, sizeof(EmitBase)))) return rc;
+    if (sharded && T.size() > 1 && (rc = group_before_produce(T))) return rc;
+    if (oon_world* w = member_of_rank(T, arank)) {
+        USE(w);
+        float2* nozzles_dev = nullptr;
+        if (nozzles_xy) {
+            if ((rc = ensure_aos(w, (size_t(n) * sizeof(float2) + sizeof(oon_body_f32) - 1) / sizeof(oon_body_f32)))) return rc;
+            nozzles_dev = reinterpret_cast<float2*>(w->aos_dev);
+            CU(w, cudaMemcpyAsync(nozzles_dev, nozzles_xy, size_t(n) * sizeof(float2), cudaMemcpyHostToDevice, w->stream));
+        }
+        w->launches += uint64_t(launch_emit(w->stream, w->soa[w->cur].d, w->d_n, w->emit_rec + erank, w->emit_rec + prank, w->emit_rec + arank, n, *cfg,
+                                            nozzles_dev, seed, kind));
+        CU(w, cudaGetLastError());
+    }
+    if (sharded && (rc = team_allgather(T, rec_of, sizeof(EmitBase)))) return rc;
+    if (oon_world* w = member_of_rank(T, erank)) {
+        USE(w);
+        w->launches += uint64_t(launch_emit_apply(w->stream, w->soa[w->cur].d, elocal, w->emit_rec + arank));
+        CU(w, cudaGetLastError());
+    }
+    EmitBase res{};
+    {
+        oon_world* w = T[0];                                // every shard holds the append rank's record by now
+        USE(w);
+        CU(w, cudaMemcpyAsync(&res, w->emit_rec + arank, sizeof res, cudaMemcpyDeviceToHost, w->stream));
+    }
+    if ((rc = team_sync(T))) return rc;
+    note_append(T, arank, res.emitted, res.emitted && kind != EMIT_SPAWN && mortal(cfg->particle_lifetime));
+    if (emitted_out) *emitted_out = res.emitted;
     return OON_OK;
 }
 
@@ -1371,184 +1710,277 @@ int oon_spawn(oon_world* w, uint64_t parent_ndx, uint64_t player_ndx, uint32_t n
     return emit_common(w, EMIT_SPAWN, player_ndx, parent_ndx, n, &cfg, nullptr, seed, nullptr, "spawn");
 }
 
-int oon_get_body(oon_world* w, uint64_t ndx, oon_body_f32* out) {
-    CHECK_W(w);
-    if (!out) return fail(w, OON_ERR_INVALID, "null output");
-    int rc = sync_count(w);
+int oon_get_body(oon_world* h, uint64_t ndx, oon_body_f32* out) {
+    CHECK_W(h);
+    if (!out) return fail(h, OON_ERR_INVALID, "null output");
+    Team& T = h->team;
+    int rc = team_sync_count(T);
     if (rc) return rc;
-    if (ndx >= w->n_total) return fail(w, OON_ERR_INVALID, "body index %llu out of range (%llu bodies)", (unsigned long long)ndx, (unsigned long long)w->n_total);
-    if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "get_body on a sharded world: use oon_download");
-    if ((rc = ensure_aos(w, 1))) return rc;
-    w->launches += launch_pack_f32(w->stream, w->soa[w->cur].d, w->aos_dev, uint32_t(ndx), 1);
-    CU(w, cudaGetLastError());
-    CU(w, cudaMemcpyAsync(out, w->aos_dev, sizeof(oon_body_f32), cudaMemcpyDeviceToHost, w->stream));
-    SYNC(w);
-    return OON_OK;
-}
-
-int oon_set_body(oon_world* w, uint64_t ndx, const oon_body_f32* in) {
-    CHECK_W(w);
-    { int qrc = quiesce_aux(w); if (qrc) return qrc; }
-    if (!in) return fail(w, OON_ERR_INVALID, "null input");
-    int rc = sync_count(w);
-    if (rc) return rc;
-    if (ndx >= w->n_total) return fail(w, OON_ERR_INVALID, "body index %llu out of range (%llu bodies)", (unsigned long long)ndx, (unsigned long long)w->n_total);
-    if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "set_body on a sharded world: re-upload the table instead");
-    if ((rc = ensure_aos(w, 1))) return rc;
-    w->has_mortals |= mortal(in->lifetime);
-    CU(w, cudaMemcpyAsync(w->aos_dev, in, sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
-    w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, uint32_t(ndx), 1, nullptr);
-    CU(w, cudaGetLastError());
-    SYNC(w);
-    w->tiles_fresh = false;
-    return OON_OK;
-}
-
-int oon_remove_body(oon_world* w, uint64_t ndx) {
-    CHECK_W(w);
-    { int qrc = quiesce_aux(w); if (qrc) return qrc; }
-    int rc = sync_count(w);
-    if (rc) return rc;
-    if (ndx >= w->n_total) return fail(w, OON_ERR_INVALID, "body index %llu out of range (%llu bodies)", (unsigned long long)ndx, (unsigned long long)w->n_total);
-    if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "remove_body on a sharded world: re-upload the table instead");
-    // erase(begin + ndx): shift the tail down by one, field by field, through the spare SoA buffer
-    const uint32_t n = w->n_local, tail = n - uint32_t(ndx) - 1;
-    SoAStorage& cur = w->soa[w->cur];
-    SoAStorage& other = w->soa[w->cur ^ 1];
-    if (other.cap < cur.cap) { if ((rc = soa_alloc(w, other, cur.cap))) return rc; }
-    if (tail) {
-#define SHIFT(f) do { CU(w, cudaMemcpyAsync(other.d.f, cur.d.f + ndx + 1, size_t(tail) * sizeof(*cur.d.f), cudaMemcpyDeviceToDevice, w->stream)); \
-                      CU(w, cudaMemcpyAsync(cur.d.f + ndx, other.d.f, size_t(tail) * sizeof(*cur.d.f), cudaMemcpyDeviceToDevice, w->stream)); } while (0)
-        SHIFT(p); SHIFT(v); SHIFT(T); SHIFT(life); SHIFT(mass); SHIFT(r); SHIFT(density); SHIFT(color); SHIFT(flags); SHIFT(thrust);
-#undef SHIFT
+    oon_world* w0 = T[0];
+    if (ndx >= w0->n_total) return fail(h, OON_ERR_INVALID, "body index %llu out of range (%llu bodies)", (unsigned long long)ndx, (unsigned long long)w0->n_total);
+    uint32_t local = 0;
+    const int orank = owner_of(w0, ndx, &local);
+    if (oon_world* w = member_of_rank(T, orank)) {
+        USE(w);
+        if ((rc = ensure_aos(w, size_t(w->nranks)))) return rc;
+        w->launches += launch_pack_f32(w->stream, w->soa[w->cur].d, w->aos_dev + (T.size() == 1 ? w->rank : 0), local, 1);
+        CU(w, cudaGetLastError());
+        if (T.size() > 1 || w->nranks == 1) {
+            CU(w, cudaMemcpyAsync(out, w->aos_dev, sizeof(oon_body_f32), cudaMemcpyDeviceToHost, w->stream));
+            SYNC(w);
+            return OON_OK;
+        }
     }
-    w->n_local = n - 1; w->n_total = n - 1;
-    CU(w, cudaMemcpyAsync(w->d_n, &w->n_local, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+    // one rank of a multi-process world: the owner's record reaches every rank through a 60-byte-per-rank all-gather
+    oon_world* w = w0;
+    if ((rc = ensure_aos(w, size_t(w->nranks)))) return rc;
+    NC(w, g_nccl.AllGather(w->aos_dev + w->rank, w->aos_dev, sizeof(oon_body_f32), ncclChar, w->comm, w->stream));
+    CU(w, cudaMemcpyAsync(out, w->aos_dev + orank, sizeof(oon_body_f32), cudaMemcpyDeviceToHost, w->stream));
     SYNC(w);
-    w->tiles_fresh = false;
-    w->order_dirty = true;
+    return OON_OK;
+}
+
+int oon_set_body(oon_world* h, uint64_t ndx, const oon_body_f32* in) {
+    CHECK_W(h);
+    Team& T = h->team;
+    int rc = team_quiesce(T);
+    if (rc) return rc;
+    if (!in) return fail(h, OON_ERR_INVALID, "null input");
+    if ((rc = team_sync_count(T))) return rc;
+    oon_world* w0 = T[0];
+    if (ndx >= w0->n_total) return fail(h, OON_ERR_INVALID, "body index %llu out of range (%llu bodies)", (unsigned long long)ndx, (unsigned long long)w0->n_total);
+    uint32_t local = 0;
+    const int orank = owner_of(w0, ndx, &local);
+    if (oon_world* w = member_of_rank(T, orank)) {
+        USE(w);
+        if ((rc = ensure_aos(w, 1))) return rc;
+        CU(w, cudaMemcpyAsync(w->aos_dev, in, sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
+        w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, local, 1, nullptr);
+        CU(w, cudaGetLastError());
+        SYNC(w);
+    }
+    for (oon_world* w : T) { w->has_mortals = w->has_mortals || mortal(in->lifetime); w->tiles_fresh = false; }
+    return OON_OK;
+}
+
+int oon_remove_body(oon_world* h, uint64_t ndx) {
+    CHECK_W(h);
+    Team& T = h->team;
+    int rc = team_quiesce(T);
+    if (rc) return rc;
+    if ((rc = team_sync_count(T))) return rc;
+    oon_world* w0 = T[0];
+    if (ndx >= w0->n_total) return fail(h, OON_ERR_INVALID, "body index %llu out of range (%llu bodies)", (unsigned long long)ndx, (unsigned long long)w0->n_total);
+    uint32_t local = 0;
+    const int orank = owner_of(w0, ndx, &local);
+    if (oon_world* w = member_of_rank(T, orank)) {
+        USE(w);
+        // erase(begin + ndx): shift the owner's tail down by one, field by field, through the spare SoA buffer
+        const uint32_t n = w->n_local, tail = n - local - 1, now = n - 1;
+        SoAStorage& cur = w->soa[w->cur];
+        SoAStorage& other = w->soa[w->cur ^ 1];
+        if (other.cap < cur.cap) { if ((rc = soa_alloc(w, other, cur.cap))) return rc; }
+        if (tail) {
+#define SHIFT(f) do { CU(w, cudaMemcpyAsync(other.d.f, cur.d.f + local + 1, size_t(tail) * sizeof(*cur.d.f), cudaMemcpyDeviceToDevice, w->stream)); \
+                      CU(w, cudaMemcpyAsync(cur.d.f + local, other.d.f, size_t(tail) * sizeof(*cur.d.f), cudaMemcpyDeviceToDevice, w->stream)); } while (0)
+            SHIFT(p); SHIFT(v); SHIFT(T); SHIFT(life); SHIFT(mass); SHIFT(r); SHIFT(density); SHIFT(color); SHIFT(flags); SHIFT(thrust);
+#undef SHIFT
+        }
+        CU(w, cudaMemcpyAsync(w->d_n, &now, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+        SYNC(w);
+    }
+    for (oon_world* w : T) {
+        if (w->nranks > 1) w->counts[size_t(orank)] -= 1u;
+        if (w->rank == orank) w->n_local -= 1u;
+        w->n_total -= 1u;
+        w->tiles_fresh = false;
+        w->order_dirty = true;
+        w->kick_valid = false;
+    }
     return OON_OK;
 }
 
 int oon_step(oon_world* w, float dt, uint32_t nsteps) {
     CHECK_W(w);
-    return step_impl(w, dt, nsteps, nullptr);
+    return team_step(w->team, dt, nsteps, nullptr);
+}
+
+// per-class device times of a team: the slowest shard's
+static int collect_profs(Team& T, std::vector<Prof>& profs, float ms[4], uint32_t launches[4]) {
+    int rc = OON_OK;
+    float out[4] = {0, 0, 0, 0};
+    for (size_t i = 0; i < T.size(); ++i) {
+        if (T[i]->parent) cudaSetDevice(T[i]->device);
+        const int crc = prof_collect(T[i], &profs[i]);
+        if (rc == OON_OK) rc = crc;
+        for (int c = 0; c < 4; ++c) out[c] = std::max(out[c], profs[i].ms[c]);
+    }
+    if (ms) std::memcpy(ms, out, sizeof out);
+    if (launches) std::memcpy(launches, profs[0].launches, sizeof profs[0].launches);
+    return rc;
 }
 
 int oon_step_profiled(oon_world* w, float dt, uint32_t nsteps, float ms[4], uint32_t launches[4]) {
     CHECK_W(w);
-    Prof prof; prof.on = true;
-    int rc = step_impl(w, dt, nsteps, &prof);
-    const int crc = prof_collect(w, &prof);
-    if (rc == OON_OK) rc = crc;
-    if (ms) std::memcpy(ms, prof.ms, sizeof prof.ms);
-    if (launches) std::memcpy(launches, prof.launches, sizeof prof.launches);
-    return rc;
+    std::vector<Prof> profs(w->team.size());
+    for (Prof& p : profs) p.on = true;
+    int rc = team_step(w->team, dt, nsteps, &profs);
+    const int crc = collect_profs(w->team, profs, ms, launches);
+    return rc ? rc : crc;
 }
 
-int oon_update_intrinsic(oon_world* w, float dt) {
-    CHECK_W(w);
-    if (!w->block) return OON_OK;
-    return do_intrinsic_pack(w, step_params(w, dt), true, nullptr);
+int oon_update_intrinsic(oon_world* h, float dt) {
+    CHECK_W(h);
+    Team& T = h->team;
+    if (!T[0]->block) return OON_OK;
+    for (oon_world* w : T) { USE(w); int rc = do_intrinsic_pack(w, step_params(w, dt), true, nullptr); if (rc) return rc; }
+    return OON_OK;
 }
 
-int oon_update_pairwise(oon_world* w, float dt) {
-    CHECK_W(w);
-    if (!w->block) return OON_OK;
-    const StepParams sp = step_params(w, dt);
+int oon_update_pairwise(oon_world* h, float dt) {
+    CHECK_W(h);
+    Team& T = h->team;
+    if (!T[0]->block) return OON_OK;
+    const StepParams sp = step_params(T[0], dt);
     int rc;
-    if (!w->tiles_fresh && (rc = do_intrinsic_pack(w, sp, false, nullptr))) return rc;
-    if ((rc = do_interact(w, sp, nullptr))) return rc;
-    ++w->order_age;
-    return do_integrate(w, sp, true, false, false, nullptr);
+    for (oon_world* w : T) { USE(w); if (!w->tiles_fresh && (rc = do_intrinsic_pack(w, sp, false, nullptr))) return rc; }
+    for (oon_world* w : T) { USE(w); if ((rc = do_interact(w, sp, nullptr))) return rc; ++w->order_age; }
+    for (oon_world* w : T) { USE(w); if ((rc = do_integrate(w, sp, true, false, false, nullptr))) return rc; }
+    return OON_OK;
 }
 
-int oon_update_global(oon_world* w, float dt) {
-    CHECK_W(w);
-    if (!w->block) return OON_OK;
-    return do_integrate(w, step_params(w, dt), false, true, false, nullptr);
+int oon_update_global(oon_world* h, float dt) {
+    CHECK_W(h);
+    Team& T = h->team;
+    if (!T[0]->block) return OON_OK;
+    for (oon_world* w : T) { USE(w); int rc = do_integrate(w, step_params(w, dt), false, true, false, nullptr); if (rc) return rc; }
+    return OON_OK;
 }
 
-int oon_sweep_expired(oon_world* w, uint64_t player_ndx) {
-    CHECK_W(w);
-    if (!w->block || !w->has_mortals) return OON_OK;
-    return do_sweep(w, uint32_t(player_ndx), nullptr);
+int oon_sweep_expired(oon_world* h, uint64_t player_ndx) {
+    CHECK_W(h);
+    Team& T = h->team;
+    if (!T[0]->block || !T[0]->has_mortals) return OON_OK;
+    return team_sweep(T, uint32_t(player_ndx), nullptr);
 }
 
 int oon_synchronize(oon_world* w) {
     CHECK_W(w);
-    SYNC(w);
-    return OON_OK;
+    return team_sync(w->team);
 }
 
 int oon_exchange_kind(const oon_world* w, int* kind) {
     if (!w || !kind) return OON_ERR_INVALID;
-    *kind = w->nranks == 1 ? OON_EXCHANGE_NONE : (w->p2p ? OON_EXCHANGE_PEER_STORES : OON_EXCHANGE_NCCL_ALLGATHER);
+    const oon_world* m = w->team[0];
+    *kind = m->nranks == 1 ? OON_EXCHANGE_NONE : (m->p2p ? OON_EXCHANGE_PEER_STORES : OON_EXCHANGE_NCCL_ALLGATHER);
     return OON_OK;
 }
 
-int oon_drain_events(oon_world* w, oon_events* out) {
-    CHECK_W(w);
-    if (!out) return fail(w, OON_ERR_INVALID, "null output");
-    unsigned long long c[C_COUNT];
-    CU(w, cudaMemcpyAsync(c, w->counters, sizeof c, cudaMemcpyDeviceToHost, w->stream));
-    CU(w, cudaMemsetAsync(w->counters, 0, sizeof(unsigned long long) * C_CAPTURE_COLL, w->stream));   // capture cursors live on
-    SYNC(w);
-    out->steps = w->steps; w->steps = 0;
-    out->collisions = c[C_COLLISIONS]; out->touches = c[C_TOUCHES]; out->player_touches = c[C_PLAYER_TOUCHES];
-    out->terminated = c[C_TERMINATED]; out->removed = c[C_REMOVED];
-    out->warp_tiles = c[C_WARP_TILES]; out->warp_tiles_checked = c[C_WARP_TILES_CHECKED];
+int oon_drain_events(oon_world* h, oon_events* out) {
+    CHECK_W(h);
+    if (!out) return fail(h, OON_ERR_INVALID, "null output");
+    Team& T = h->team;
+    std::vector<unsigned long long> c(size_t(C_COUNT) * T.size(), 0ull);
+    for (size_t i = 0; i < T.size(); ++i) {
+        oon_world* w = T[i];
+        USE(w);
+        CU(w, cudaMemcpyAsync(&c[size_t(C_COUNT) * i], w->counters, sizeof(unsigned long long) * C_COUNT, cudaMemcpyDeviceToHost, w->stream));
+        CU(w, cudaMemsetAsync(w->counters, 0, sizeof(unsigned long long) * C_CAPTURE_COLL, w->stream));   // capture cursors live on
+    }
+    int rc = team_sync(T);
+    if (rc) return rc;
+    std::memset(out, 0, sizeof *out);
+    out->steps = T[0]->steps;
+    for (size_t i = 0; i < T.size(); ++i) {                 // each visit is counted on exactly one shard (the target's owner)
+        const unsigned long long* k = &c[size_t(C_COUNT) * i];
+        T[i]->steps = 0;
+        out->collisions += k[C_COLLISIONS]; out->touches += k[C_TOUCHES]; out->player_touches += k[C_PLAYER_TOUCHES];
+        out->terminated += k[C_TERMINATED]; out->removed += k[C_REMOVED];
+        out->warp_tiles += k[C_WARP_TILES]; out->warp_tiles_checked += k[C_WARP_TILES_CHECKED];
+    }
     return OON_OK;
 }
 
-int oon_timer_start(oon_world* w) {
-    CHECK_W(w);
-    CU(w, cudaEventRecord(w->ev_start, w->stream));
+int oon_timer_start(oon_world* h) {
+    CHECK_W(h);
+    for (oon_world* w : h->team) { USE(w); CU(w, cudaEventRecord(w->ev_start, w->stream)); }
     return OON_OK;
 }
-int oon_timer_stop(oon_world* w, float* elapsed_ms) {
-    CHECK_W(w);
-    if (!elapsed_ms) return fail(w, OON_ERR_INVALID, "null output");
-    CU(w, cudaEventRecord(w->ev_stop, w->stream));
-    CU(w, cudaEventSynchronize(w->ev_stop));
-    CU(w, cudaEventElapsedTime(elapsed_ms, w->ev_start, w->ev_stop));
-    return peers_ok(w);
+int oon_timer_stop(oon_world* h, float* elapsed_ms) {
+    CHECK_W(h);
+    if (!elapsed_ms) return fail(h, OON_ERR_INVALID, "null output");
+    *elapsed_ms = 0.f;
+    for (oon_world* w : h->team) { USE(w); CU(w, cudaEventRecord(w->ev_stop, w->stream)); }
+    for (oon_world* w : h->team) {
+        USE(w);
+        float ms = 0.f;
+        CU(w, cudaEventSynchronize(w->ev_stop));
+        CU(w, cudaEventElapsedTime(&ms, w->ev_start, w->ev_stop));
+        *elapsed_ms = std::max(*elapsed_ms, ms);           // a group's frame ends when its slowest shard does
+        int rc = peers_ok(w);
+        if (rc) return rc;
+    }
+    return OON_OK;
 }
 
-static int bench_frames_impl(oon_world* w, float dt, uint32_t nsteps, uint64_t flush_bytes, double* ms_sum, Prof* prof) {
-    CHECK_W(w);
-    if (!ms_sum) return fail(w, OON_ERR_INVALID, "null output");
+static int bench_frames_impl(oon_world* h, float dt, uint32_t nsteps, uint64_t flush_bytes, double* ms_sum, std::vector<Prof>* profs) {
+    CHECK_W(h);
+    if (!ms_sum) return fail(h, OON_ERR_INVALID, "null output");
     *ms_sum = 0.0;
     if (!nsteps) return OON_OK;
-    void* flush = nullptr;
-    if (flush_bytes) CU(w, cudaMalloc(&flush, flush_bytes));
-    std::vector<cudaEvent_t> ev(size_t(2) * nsteps, nullptr);
+    Team& T = h->team;
+    const size_t M = T.size();
+    std::vector<void*> flush(M, nullptr);
+    std::vector<cudaEvent_t> ev(size_t(2) * nsteps * M, nullptr);
     int rc = OON_OK;
-    for (auto& e : ev) if (cudaEventCreate(&e) != cudaSuccess) { rc = fail(w, OON_ERR_CUDA, "cudaEventCreate failed"); break; }
-    for (uint32_t k = 0; k < nsteps && rc == OON_OK; ++k) {
-        if (flush && cudaMemsetAsync(flush, int(k & 0xff), flush_bytes, w->stream) != cudaSuccess) { rc = fail(w, OON_ERR_CUDA, "flush memset failed"); break; }
-        if (flush && w->nranks > 1) {
-            // The ranks of a sharded world wait for each other inside the frame: line them up again after the untimed flush
-            // (a one-word all-gather on the stream), or the slowest rank's flush would be charged to everybody's frame.
-            if (g_nccl.AllGather(static_cast<char*>(w->ipc_stage) + size_t(w->rank) * 4, w->ipc_stage, 4, ncclChar, w->comm, w->stream) != ncclSuccess) {
-                rc = fail(w, OON_ERR_NCCL, "alignment all-gather failed"); break;
-            }
+    auto body = [&]() -> int {
+        for (size_t i = 0; i < M; ++i) {
+            USE(T[i]);
+            if (flush_bytes) CU(T[i], cudaMalloc(&flush[i], flush_bytes));
+            for (uint32_t k = 0; k < 2 * nsteps; ++k) CU(T[i], cudaEventCreate(&ev[(size_t(k) * M) + i]));
         }
-        if (cudaEventRecord(ev[2 * k], w->stream) != cudaSuccess) { rc = fail(w, OON_ERR_CUDA, "cudaEventRecord failed"); break; }
-        rc = step_impl(w, dt, 1, prof);
-        if (rc == OON_OK && cudaEventRecord(ev[2 * k + 1], w->stream) != cudaSuccess) rc = fail(w, OON_ERR_CUDA, "cudaEventRecord failed");
-    }
-    if (rc == OON_OK) rc = sync_main(w);
-    if (prof) { const int crc = prof_collect(w, prof); if (rc == OON_OK) rc = crc; }
-    if (rc == OON_OK) {
         for (uint32_t k = 0; k < nsteps; ++k) {
-            float ms = 0.f;
-            if (cudaEventElapsedTime(&ms, ev[2 * k], ev[2 * k + 1]) != cudaSuccess) { rc = fail(w, OON_ERR_CUDA, "cudaEventElapsedTime failed"); break; }
-            *ms_sum += double(ms);
+            for (size_t i = 0; i < M; ++i) {
+                oon_world* w = T[i];
+                USE(w);
+                if (flush_bytes) CU(w, cudaMemsetAsync(flush[i], int(k & 0xff), flush_bytes, w->stream));
+                // The shards of a world wait for each other inside the frame: line them up again after the untimed flush (a
+                // one-word all-gather / a round of event waits), or the slowest shard's flush would be charged to everybody's frame.
+                if (flush_bytes && M == 1 && w->nranks > 1)
+                    NC(w, g_nccl.AllGather(static_cast<char*>(w->ipc_stage) + size_t(w->rank) * 4, w->ipc_stage, 4, ncclChar, w->comm, w->stream));
+                if (M > 1) CU(w, cudaEventRecord(w->ev_grp, w->stream));
+            }
+            for (size_t i = 0; i < M; ++i) {
+                oon_world* w = T[i];
+                USE(w);
+                if (M > 1) for (oon_world* g : T) if (g != w) CU(w, cudaStreamWaitEvent(w->stream, g->ev_grp, 0));
+                CU(w, cudaEventRecord(ev[(size_t(2 * k) * M) + i], w->stream));
+            }
+            int src = team_step(T, dt, 1, profs);
+            if (src) return src;
+            for (size_t i = 0; i < M; ++i) { USE(T[i]); CU(T[i], cudaEventRecord(ev[(size_t(2 * k + 1) * M) + i], T[i]->stream)); }
         }
+        int src = team_sync(T);
+        if (src) return src;
+        for (uint32_t k = 0; k < nsteps; ++k) {
+            float worst = 0.f;
+            for (size_t i = 0; i < M; ++i) {
+                USE(T[i]);
+                float ms = 0.f;
+                CU(T[i], cudaEventElapsedTime(&ms, ev[(size_t(2 * k) * M) + i], ev[(size_t(2 * k + 1) * M) + i]));
+                worst = std::max(worst, ms);
+            }
+            *ms_sum += double(worst);
+        }
+        return OON_OK;
+    };
+    rc = body();
+    for (size_t i = 0; i < M; ++i) {
+        if (T[i]->parent) cudaSetDevice(T[i]->device);
+        if (rc != OON_OK) cudaStreamSynchronize(T[i]->stream);
+        for (uint32_t k = 0; k < 2 * nsteps; ++k) if (ev[(size_t(k) * M) + i]) cudaEventDestroy(ev[(size_t(k) * M) + i]);
+        if (flush[i]) cudaFree(flush[i]);
     }
-    for (auto& e : ev) if (e) cudaEventDestroy(e);
-    if (flush) cudaFree(flush);
     return rc;
 }
 
@@ -1557,16 +1989,18 @@ int oon_bench_frames(oon_world* w, float dt, uint32_t nsteps, uint64_t flush_byt
 }
 
 int oon_bench_frames_profiled(oon_world* w, float dt, uint32_t nsteps, uint64_t flush_bytes, double* ms_sum, float ms[4], uint32_t launches[4]) {
-    Prof prof; prof.on = true;
-    const int rc = bench_frames_impl(w, dt, nsteps, flush_bytes, ms_sum, &prof);
-    if (ms) std::memcpy(ms, prof.ms, sizeof prof.ms);
-    if (launches) std::memcpy(launches, prof.launches, sizeof prof.launches);
-    return rc;
+    if (!w) return OON_ERR_INVALID;
+    std::vector<Prof> profs(w->team.size());
+    for (Prof& p : profs) p.on = true;
+    const int rc = bench_frames_impl(w, dt, nsteps, flush_bytes, ms_sum, &profs);
+    const int crc = collect_profs(w->team, profs, ms, launches);
+    return rc ? rc : crc;
 }
 
 int oon_launch_count(const oon_world* w, uint64_t* n_out) {
     if (!w || !n_out) return OON_ERR_INVALID;
-    *n_out = w->launches;
+    *n_out = 0;
+    for (const oon_world* m : w->team) *n_out += m->launches;
     return OON_OK;
 }
 
@@ -1587,67 +2021,93 @@ int oon_measure_copy_bandwidth(int device, double* gbs_out) {
     return OON_OK;
 }
 
-int oon_debug_capture_pairs(oon_world* w, uint64_t capacity) {
-    CHECK_W(w);
-    SYNC(w);
-    cudaFree(w->cap.coll); cudaFree(w->cap.touch);
-    w->cap = CaptureBuf{};
-    if (capacity) {
-        if (capacity > 0x7fffffffull) return fail(w, OON_ERR_INVALID, "capture capacity too large");
-        int rc;
-        if ((rc = dev_alloc(w, &w->cap.coll, capacity))) return rc;
-        if ((rc = dev_alloc(w, &w->cap.touch, capacity))) return rc;
-        w->cap.capacity = uint32_t(capacity);
-    }
-    CU(w, cudaMemset(w->counters + C_CAPTURE_COLL, 0, 2 * sizeof(unsigned long long)));
-    w->kick_valid = false;
-    return OON_OK;
-}
-
-int oon_debug_fetch_pairs(oon_world* w, int which, uint32_t* pairs, uint64_t capacity, uint64_t* n_out) {
-    CHECK_W(w);
-    if (which != 0 && which != 1) return fail(w, OON_ERR_INVALID, "which must be 0 or 1");
-    if (!w->cap.capacity) return fail(w, OON_ERR_INVALID, "pair capture is off");
-    unsigned long long cnt = 0;
-    const int ci = which == 0 ? C_CAPTURE_COLL : C_CAPTURE_TOUCH;
-    CU(w, cudaMemcpyAsync(&cnt, w->counters + ci, sizeof cnt, cudaMemcpyDeviceToHost, w->stream));
-    SYNC(w);
-    if (n_out) *n_out = cnt;
-    if (cnt > w->cap.capacity) return fail(w, OON_ERR_CAPACITY, "pair capture overflowed: %llu pairs, capacity %u", cnt, w->cap.capacity);
-    if (cnt > capacity) return fail(w, OON_ERR_CAPACITY, "output too small for %llu pairs", cnt);
-    if (cnt) {
-        if (!pairs) return fail(w, OON_ERR_INVALID, "null output");
-        CU(w, cudaMemcpyAsync(pairs, which == 0 ? w->cap.coll : w->cap.touch, size_t(cnt) * sizeof(uint2), cudaMemcpyDeviceToHost, w->stream));
-    }
-    CU(w, cudaMemsetAsync(w->counters + ci, 0, sizeof(unsigned long long), w->stream));
-    SYNC(w);
-    return OON_OK;
-}
-
-int oon_debug_fetch_kick(oon_world* w, float* dv, uint64_t capacity, uint64_t* n_out) {
-    CHECK_W(w);
-    if (!w->kick_valid) return fail(w, OON_ERR_INVALID, "no kick recorded: enable oon_debug_capture_pairs and run a pairwise pass first");
-    if (w->nranks > 1) return fail(w, OON_ERR_UNSUPPORTED, "kick trace on a sharded world");
-    const uint64_t n = w->n_local;
-    if (n_out) *n_out = n;
-    if (n > capacity) return fail(w, OON_ERR_CAPACITY, "output too small for %llu bodies", (unsigned long long)n);
-    if (n) CU(w, cudaMemcpyAsync(dv, w->kick, size_t(n) * sizeof(float2), cudaMemcpyDeviceToHost, w->stream));
-    SYNC(w);
-    return OON_OK;
-}
-
-int oon_debug_fetch_removed(oon_world* w, uint32_t* idx, uint64_t capacity, uint64_t* n_out) {
-    CHECK_W(w);
-    uint32_t cnt = 0;
-    CU(w, cudaMemcpyAsync(&cnt, w->d_removed_count, sizeof cnt, cudaMemcpyDeviceToHost, w->stream));
-    SYNC(w);
-    if (n_out) *n_out = cnt;
-    if (cnt > capacity) return fail(w, OON_ERR_CAPACITY, "output too small for %u indices", cnt);
-    if (cnt) {
-        if (!idx) return fail(w, OON_ERR_INVALID, "null output");
-        CU(w, cudaMemcpyAsync(idx, w->removed_idx, size_t(cnt) * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+int oon_debug_capture_pairs(oon_world* h, uint64_t capacity) {
+    CHECK_W(h);
+    if (capacity > 0x7fffffffull) return fail(h, OON_ERR_INVALID, "capture capacity too large");
+    for (oon_world* w : h->team) {
+        USE(w);
         SYNC(w);
+        cudaFree(w->cap.coll); cudaFree(w->cap.touch);
+        w->cap = CaptureBuf{};
+        if (capacity) {
+            int rc;
+            if ((rc = dev_alloc(w, &w->cap.coll, capacity))) return rc;
+            if ((rc = dev_alloc(w, &w->cap.touch, capacity))) return rc;
+            w->cap.capacity = uint32_t(capacity);
+        }
+        CU(w, cudaMemset(w->counters + C_CAPTURE_COLL, 0, 2 * sizeof(unsigned long long)));
+        w->kick_valid = false;
     }
+    return OON_OK;
+}
+
+int oon_debug_fetch_pairs(oon_world* h, int which, uint32_t* pairs, uint64_t capacity, uint64_t* n_out) {
+    CHECK_W(h);
+    if (which != 0 && which != 1) return fail(h, OON_ERR_INVALID, "which must be 0 or 1");
+    const int ci = which == 0 ? C_CAPTURE_COLL : C_CAPTURE_TOUCH;
+    uint64_t total = 0;
+    for (oon_world* w : h->team) {                          // a group's lists are concatenated (each visit is recorded by the target's owner)
+        USE(w);
+        if (!w->cap.capacity) return fail(h, OON_ERR_INVALID, "pair capture is off");
+        unsigned long long cnt = 0;
+        CU(w, cudaMemcpyAsync(&cnt, w->counters + ci, sizeof cnt, cudaMemcpyDeviceToHost, w->stream));
+        SYNC(w);
+        if (cnt > w->cap.capacity) { if (n_out) *n_out = total + cnt; return fail(h, OON_ERR_CAPACITY, "pair capture overflowed: %llu pairs, capacity %u", cnt, w->cap.capacity); }
+        if (total + cnt > capacity) { if (n_out) *n_out = total + cnt; return fail(h, OON_ERR_CAPACITY, "output too small for %llu pairs", (unsigned long long)(total + cnt)); }
+        if (cnt) {
+            if (!pairs) return fail(h, OON_ERR_INVALID, "null output");
+            CU(w, cudaMemcpyAsync(pairs + 2 * total, which == 0 ? w->cap.coll : w->cap.touch, size_t(cnt) * sizeof(uint2), cudaMemcpyDeviceToHost, w->stream));
+        }
+        CU(w, cudaMemsetAsync(w->counters + ci, 0, sizeof(unsigned long long), w->stream));
+        SYNC(w);
+        total += cnt;
+    }
+    if (n_out) *n_out = total;
+    return OON_OK;
+}
+
+int oon_debug_fetch_kick(oon_world* h, float* dv, uint64_t capacity, uint64_t* n_out) {
+    CHECK_W(h);
+    Team& T = h->team;
+    if (T.size() == 1 && T[0]->nranks > 1) return fail(h, OON_ERR_UNSUPPORTED, "kick trace on one rank of a multi-process world");
+    int rc = team_sync_count(T);
+    if (rc) return rc;
+    const uint64_t n = T[0]->n_total;
+    if (n_out) *n_out = n;
+    if (n > capacity) return fail(h, OON_ERR_CAPACITY, "output too small for %llu bodies", (unsigned long long)n);
+    for (oon_world* w : T) {
+        USE(w);
+        if (!w->kick_valid) return fail(h, OON_ERR_INVALID, "no kick recorded: enable oon_debug_capture_pairs and run a pairwise pass first");
+        if (w->n_local) CU(w, cudaMemcpyAsync(dv + 2 * rank_first(w, w->rank), w->kick, size_t(w->n_local) * sizeof(float2), cudaMemcpyDeviceToHost, w->stream));
+    }
+    return team_sync(T);
+}
+
+// Indices erased by the last sweep, at the time of removal like the oracle's trace (OON.cpp:1089-1095 erases in ascending
+// order, so when a body goes every rank before it has finished: its index then = survivors of the earlier ranks + its local
+// index at removal).
+int oon_debug_fetch_removed(oon_world* h, uint32_t* idx, uint64_t capacity, uint64_t* n_out) {
+    CHECK_W(h);
+    Team& T = h->team;
+    int rc = team_sync_count(T);
+    if (rc) return rc;
+    uint64_t total = 0;
+    for (oon_world* w : T) {
+        USE(w);
+        uint32_t cnt = 0;
+        CU(w, cudaMemcpyAsync(&cnt, w->d_removed_count, sizeof cnt, cudaMemcpyDeviceToHost, w->stream));
+        SYNC(w);
+        if (total + cnt > capacity) { if (n_out) *n_out = total + cnt; return fail(h, OON_ERR_CAPACITY, "output too small for %llu indices", (unsigned long long)(total + cnt)); }
+        if (cnt) {
+            if (!idx) return fail(h, OON_ERR_INVALID, "null output");
+            CU(w, cudaMemcpyAsync(idx + total, w->removed_idx, size_t(cnt) * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+            SYNC(w);
+            const uint32_t off = uint32_t(rank_first(w, w->rank));
+            for (uint32_t k = 0; k < cnt; ++k) idx[total + k] += off;
+        }
+        total += cnt;
+    }
+    if (n_out) *n_out = total;
     return OON_OK;
 }
 

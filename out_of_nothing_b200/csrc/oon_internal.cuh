@@ -124,11 +124,25 @@ int launch_unpack_f32(cudaStream_t st, const oon_body_f32* aos, BodySoA soa, uin
 int launch_pack_f32(cudaStream_t st, BodySoA soa, oon_body_f32* aos, uint32_t first, uint32_t count);
 
 // The reference's three body-creating loops on the device: up to n new bodies appended at index *d_n (which is
-// advanced); *emitted_out = how many.  emitter = the body they are created around (spawn: the player), parent = the
-// body a spawned one inherits T and v from.
+// advanced).  The body they are created around (spawn: the player) and the body a spawned one inherits T and v from are
+// passed as EmitBase records, so that they may live on another rank than the tail of the table: launch_emit_fetch (owner
+// ranks) -> records travel -> launch_emit (append rank; fills the result part of *result) -> launch_emit_apply (emitter's owner).
+struct EmitBase {
+    float2 ep, ev;                   // emitter: position, velocity
+    float er, em, edens;             // emitter: radius, mass, density
+    float pT;                        // parent: temperature
+    float2 pv;                       // parent: velocity
+    float new_mass, new_r;           // result: the emitter after the burst ...
+    uint32_t write_mass, write_r;    // ... and which of the two fields changed
+    uint32_t emitted;                // result: particles appended
+    uint32_t _pad;
+};
+static_assert(sizeof(EmitBase) == 64, "EmitBase is one 64-byte record of the all-gather staging");
 enum { EMIT_PARTICLES = 0, EMIT_CHEMTRAIL = 1, EMIT_SPAWN = 2 };
-int launch_emit(cudaStream_t st, BodySoA soa, uint32_t* d_n, uint32_t emitter, uint32_t parent, uint32_t n, const oon_emitter_cfg& cfg,
-                const float2* nozzles, unsigned long long seed, int kind, uint32_t* emitted_out);
+int launch_emit_fetch(cudaStream_t st, BodySoA soa, int emitter_local /* -1: not mine */, int parent_local /* -1: not mine */, EmitBase* out);
+int launch_emit(cudaStream_t st, BodySoA soa, uint32_t* d_n, const EmitBase* emitter, const EmitBase* parent, EmitBase* result, uint32_t n,
+                const oon_emitter_cfg& cfg, const float2* nozzles, unsigned long long seed, int kind);
+int launch_emit_apply(cudaStream_t st, BodySoA soa, uint32_t emitter_local, const EmitBase* result);
 
 // slot order: identity, or Hilbert-curve order of the positions (FAST all-pairs mode)
 size_t order_temp_bytes(uint32_t slots);
@@ -198,8 +212,8 @@ int launch_sweep_compact(cudaStream_t st, BodySoA src, BodySoA dst, uint32_t* d_
                          void* temp, size_t temp_bytes, int* scratch_i32, uint32_t* removed_idx, uint32_t removed_cap,
                          uint32_t* d_removed_count, unsigned long long* counters);
 
-// render read set: {x, y, r} per body
-int launch_render_pack(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint32_t slots, float* xyr);
+// render read set: {x, y, r} per body + the colour word
+int launch_render_pack(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint32_t slots, float* xyr, uint32_t* colors);
 
 // microbenchmarks
 float measure_fp32_peak_tflops(cudaStream_t st);

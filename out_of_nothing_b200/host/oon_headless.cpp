@@ -5,7 +5,8 @@
 // i.e. --headless --cfg= --interact --friction= --fixed-dt= --fps-limit= --loop-cap= --exit-on-finish --session=
 //      --session-save-as= --no-save-compressed --bodies= --g-mode=R|H|0 --log-level=   (unknown engine flags are ignored)
 // and follows OONApp::init_world_hook (src/app/OON.cpp:241-292) for the initial world.
-// Extras: --math=fast|exact, --device=N, --loop-mode=half|full, --convert-only (load + save, no device), --report.
+// Extras: --math=fast|exact, --device=N, --gpus=N (one world over N GPUs of this process: oon_create_multi), --loop-mode=half|full,
+//         --convert-only (load + save, no device), --report.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -68,7 +69,7 @@ void add_random_body_near(World& w, EntityID base_id, uint64_t index) {   // OON
 int usage() {
     std::puts("oon_headless --session=START.state --interact --friction=0.01 --fixed-dt=0.033 --loop-cap=20 --exit-on-finish\n"
               "             --session-save-as=END.state --no-save-compressed [--math=exact|fast] [--g-mode=R|H|0] [--bodies=N]\n"
-              "             [--loop-mode=half|full] [--device=0] [--report] [--convert-only]");
+              "             [--loop-mode=half|full] [--device=0] [--gpus=1] [--report] [--convert-only]");
     return 2;
 }
 
@@ -90,11 +91,17 @@ int main(int argc, char** argv) {
             return 0;
         }
 
-        World world(std::atoi(args.get("device", "0").c_str()));
-        // ---- init_world_hook (OON.cpp:241-292)
+        const int first_device = std::atoi(args.get("device", "0").c_str());
+        const int ngpus = std::max(1, std::atoi(args.get("gpus", "1").c_str()));
+        std::vector<int> devices;
+        for (int g = 0; g < ngpus; ++g) devices.push_back(first_device + g);
+        World world(devices);                      // one GPU: oon_create; several: oon_create_multi (single process, single mutator)
+        bool load_failed = false;
+        // ---- init_world_hook (OON.cpp:241-292), run through World::init() like the engine does (World.cpp:82-90)
+        world.init_world_hook = [&](World& world) {
         if (args.has("session") && !args.get("session").empty()) {
             std::ifstream in(args.get("session"), std::ios::binary);
-            if (!in || !World::load(in, &world)) { std::fprintf(stderr, "Failed to load session '%s'\n", args.get("session").c_str()); return 1; }
+            if (!in || !World::load(in, &world)) { std::fprintf(stderr, "Failed to load session '%s'\n", args.get("session").c_str()); load_failed = true; }
         } else {
             Entity player;                         // "Player Superglobe" (test/OON.cfg:16-18)
             player.density = 550.f; player.mass = 1e27f; player.color = 0xffff20;
@@ -110,6 +117,9 @@ int main(int argc, char** argv) {
                 Entity b; b.p = {-R * 1.6f, R * 1.2f}; b.v = {-R * 1.8f, -R * 1.5f}; b.color = 0x3060ff; b.mass = 3e24f; world.add_body(b);
             }
         }
+        };
+        world.init();
+        if (load_failed) return 1;
         if (args.has("interact")) world.props.interact_n2n = true;
         if (args.has("friction")) world.props.friction = std::stof(args.get("friction"));
         if (args.has("g-mode")) {                  // OONConfig.cpp:82-91
@@ -137,9 +147,9 @@ int main(int argc, char** argv) {
         if (args.has("report")) {
             const oon_events ev = world.drain_events();
             const double inter = world.props.interact_n2n ? double(cap) * double(n0) * double(n0 - 1) : double(cap) * double(n0 - 1);
-            std::printf("{\"frames\": %ld, \"bodies_start\": %zu, \"bodies_end\": %zu, \"seconds\": %.6f, \"steps_per_sec\": %.3f, "
+            std::printf("{\"gpus\": %d, \"frames\": %ld, \"bodies_start\": %zu, \"bodies_end\": %zu, \"seconds\": %.6f, \"steps_per_sec\": %.3f, "
                         "\"interactions_per_sec\": %.6e, \"collisions\": %llu, \"touches\": %llu, \"removed\": %llu}\n",
-                        cap, n0, n1, secs, cap / secs, inter / secs, (unsigned long long)ev.collisions, (unsigned long long)ev.touches,
+                        world.device_count(), cap, n0, n1, secs, cap / secs, inter / secs, (unsigned long long)ev.collisions, (unsigned long long)ev.touches,
                         (unsigned long long)ev.removed);
         }
         return 0;

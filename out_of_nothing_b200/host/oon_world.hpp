@@ -16,6 +16,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <iosfwd>
 #include <stdexcept>
 #include <string>
@@ -89,17 +90,42 @@ public:
     explicit World(int device = 0) {
         if (int rc = oon_create(device, &h_)) throw std::runtime_error(std::string("oon_create: ") + oon_last_error(nullptr) + " (" + std::to_string(rc) + ")");
     }
+    // One world over several GPUs of this process (the reference is one process with a single mutator, main.cpp:88-91):
+    // same interface, the shards are the library's business.
+    explicit World(std::vector<int> const& devices) {
+        if (int rc = oon_create_multi(devices.data(), int(devices.size()), &h_))
+            throw std::runtime_error(std::string("oon_create_multi: ") + oon_last_error(nullptr) + " (" + std::to_string(rc) + ")");
+    }
     ~World() { if (h_) oon_destroy(h_); }
     World(const World&) = delete;
     World& operator=(const World&) = delete;
 
-    // ---- setup (World.cpp:55-78) -------------------------------------------------------------
+    // ---- setup (World.hpp:115-121, World.cpp:55-90) --------------------------------------------
+    // init(): the reference's World::init() only calls back into the app (`app.init_world_hook()`, World.cpp:82-90); the
+    // mirror has no app object, so the host installs the hook it wants run (oon_headless: OONApp::init_world_hook's body).
+    std::function<void(World&)> init_world_hook;
+    void init() { if (init_world_hook) init_world_hook(*this); }
+
     EntityID add_body(Entity const& obj) {
         pull();
         bodies_.push_back(obj);
         bodies_.back().recalc();
         host_dirty_ = true;
         return bodies_.size() - 1;
+    }
+    EntityID add_body(Entity&& obj) {                      // World.cpp:64-70: recalc the throw-away original, then append
+        obj.recalc();
+        pull();
+        bodies_.push_back(obj);
+        host_dirty_ = true;
+        return bodies_.size() - 1;
+    }
+    // World.cpp:468-482.  The two-argument overload is the reference's stub (always false); the decision the update
+    // itself takes is the three-argument one — here for host code that wants to ask the same question (GUI picking, tests);
+    // the device evaluates it per visited pair with the identical IEEE sequence (exact_decide, csrc/oon_kernels.cu).
+    bool is_colliding(Entity const* /*obj1*/, Entity const* /*obj2*/) const { return false; }
+    bool is_colliding(Entity const* obj1, Entity const* obj2, float distance) const {
+        return props.collision_mode == CollisionMode::Off ? false : distance <= obj1->r + obj2->r;
     }
     void remove_body(EntityID ndx) {
         pull();
@@ -156,6 +182,7 @@ public:
     bool save(std::ostream& out, const char* version = nullptr);
     static bool load(std::istream& in, World* result);
 
+    int device_count() const { int n = 1; oon_device_count(h_, &n); return n; }
     oon_world* handle() { return h_; }
 
 private:

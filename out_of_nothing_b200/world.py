@@ -50,12 +50,17 @@ class Properties:
 
 
 class World:
-    """One world on one GPU, or one shard of a world sharded over ``nranks`` processes."""
+    """One world on one GPU, one world over several GPUs of this process (``devices=[...]``), or one shard of a world
+    sharded over ``nranks`` processes."""
 
-    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1, nccl_id: Optional[bytes] = None):
+    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1, nccl_id: Optional[bytes] = None, devices=None):
         self._L = capi.load()
         self._h = ctypes.c_void_p()
-        if nranks == 1:
+        if devices is not None:                              # single-process multi-GPU handle (oon_create_multi)
+            arr = (ctypes.c_int * len(devices))(*devices)
+            rc = self._L.oon_create_multi(arr, len(devices), ctypes.byref(self._h))
+            device, rank, nranks = devices[0], 0, 1           # to its caller the group is one rank that owns the whole table
+        elif nranks == 1:
             rc = self._L.oon_create(device, ctypes.byref(self._h))
         else:
             rc = self._L.oon_create_sharded(device, rank, nranks, nccl_id, ctypes.byref(self._h))
@@ -151,15 +156,14 @@ class World:
         self._check(self._L.oon_upload_local(self._h, ptr, count, n_total))
 
     def download_local(self):
-        """-> (first global index, this rank's bodies)."""
-        cap = max(1, self.local_range(max(1, self.entity_count()))[1])
-        out = np.zeros(cap, BODY_F32)
+        """-> (first global index, this rank's bodies).  Collective on a multi-process world whose bodies can expire."""
         first, got = ctypes.c_uint64(), ctypes.c_uint64()
-        rc = self._L.oon_download_local(self._h, out.ctypes.data, cap, ctypes.byref(first), ctypes.byref(got))
-        if rc == capi.ERR_CAPACITY:                          # ragged blocks after sweeps: a rank may hold more than the even share
-            out = np.zeros(got.value, BODY_F32)
-            rc = self._L.oon_download_local(self._h, out.ctypes.data, got.value, ctypes.byref(first), ctypes.byref(got))
-        self._check(rc)
+        rc = self._L.oon_download_local(self._h, None, 0, ctypes.byref(first), ctypes.byref(got))     # how many? (ragged blocks after sweeps)
+        if rc not in (capi.OK, capi.ERR_CAPACITY):
+            self._check(rc)
+        out = np.zeros(got.value, BODY_F32)
+        if got.value:
+            self._check(self._L.oon_download_local(self._h, out.ctypes.data, got.value, ctypes.byref(first), ctypes.byref(got)))
         return first.value, out[: got.value]
 
     def download_local_ptr(self, ptr: int, capacity: int):
@@ -176,6 +180,19 @@ class World:
         got = ctypes.c_uint64()
         self._check(self._L.oon_download_render(self._h, out.ctypes.data, n, ctypes.byref(got)))
         return out[: got.value]
+
+    def download_render_rgb(self):
+        """-> ({x, y, r} per body, colour word per body): everything render_scene reads (OONMainDisplay_sfml.cpp:181-211)."""
+        n = self.entity_count()
+        xyr, col = np.zeros((n, 3), np.float32), np.zeros(n, np.uint32)
+        got = ctypes.c_uint64()
+        self._check(self._L.oon_download_render_rgb(self._h, xyr.ctypes.data, col.ctypes.data, n, ctypes.byref(got)))
+        return xyr[: got.value], col[: got.value]
+
+    def device_count(self) -> int:
+        n = ctypes.c_int()
+        self._check(self._L.oon_device_count(self._h, ctypes.byref(n)))
+        return n.value
 
     def download_render_begin(self, ptr: int, capacity: int):
         """Start the render read-back ({x, y, r} per body) into pinned host memory at ``ptr``; returns at once."""
