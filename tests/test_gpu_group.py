@@ -64,7 +64,8 @@ def test_group_is_bit_identical_to_one_gpu(mode, name):
             pytest.skip("EXACT at 50k adds nothing over 20k")
         bodies, cfg = synth.make("c4_cloud_100k", n=n)
         props, steps = cfg["props"], 6
-    one, grp = pair(bodies, props, mode, capture=1 << 20)
+    small = len(bodies) < 5000                                # (a 20k-body cloud has millions of colliding pair-frames: counts only)
+    one, grp = pair(bodies, props, mode, capture=(1 << 20) if small else 0)
     assert grp.device_count() == ndev() and one.device_count() == 1
     assert grp.exchange_kind() == "peer_stores"
     one.step(DT, steps); grp.step(DT, steps)
@@ -73,8 +74,9 @@ def test_group_is_bit_identical_to_one_gpu(mode, name):
     xa, ca = one.download_render_rgb(); xb, cb = grp.download_render_rgb()
     assert xa.tobytes() == xb.tobytes() and ca.tobytes() == cb.tobytes()
     assert (xa[:, :2] == a["p"]).all() and (xa[:, 2] == a["r"]).all() and (ca == a["color"]).all()
-    assert pair_list(one.debug_fetch_pairs(0)) == pair_list(grp.debug_fetch_pairs(0))
-    assert pair_list(one.debug_fetch_pairs(1)) == pair_list(grp.debug_fetch_pairs(1))
+    if small:
+        assert pair_list(one.debug_fetch_pairs(0)) == pair_list(grp.debug_fetch_pairs(0))
+        assert pair_list(one.debug_fetch_pairs(1)) == pair_list(grp.debug_fetch_pairs(1))
     ea, eb = one.drain_events(), grp.drain_events()
     for k in ("steps", "collisions", "touches", "player_touches", "terminated", "removed"):
         assert ea[k] == eb[k], k
@@ -200,6 +202,7 @@ def test_group_timing_hooks_and_errors():
     _, prof, launches = grp.bench_frames_profiled(cfg["dt"], 2, 64 << 20)
     assert prof["interact"] > 0 and launches["interact"] == 2
     grp.timer_start(); grp.step(cfg["dt"], 2); assert grp.timer_stop() > 0
+    one.step(cfg["dt"], 4)                                            # the same number of frames on both
     assert one.download().tobytes() == grp.download().tobytes()
     assert grp.launch_count() > one.launch_count()
     with pytest.raises(capi.OonError):

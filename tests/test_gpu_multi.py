@@ -184,3 +184,33 @@ def test_sharded_fast_frame_on_ragged_blocks_keeps_every_decision(tmp_path, kind
         assert (a[f] == b[f]).all(), f
     rms = np.sqrt((b["v"].astype(np.float64) ** 2).sum(axis=1).mean())
     assert np.sqrt(((a["v"].astype(np.float64) - b["v"]) ** 2).sum(axis=1)).max() <= 5e-5 * rms
+
+
+@pytest.mark.skipif(gpu_count() < 2, reason="needs 2 GPUs")
+def test_sharded_table_edits_and_emitters_equal_one_gpu(tmp_path):
+    """One process per GPU: add / remove / set / get and the emitters are routed to the owning rank (every rank makes the same
+    call); EXACT mode stays bit-identical to one GPU through appends that overflow the tail shard, removals and expiring exhaust."""
+    import multi_worker
+    outs = {}
+    for nranks in (1, min(2, gpu_count())):
+        out = str(tmp_path / ("edits_%d_" % nranks)) + "%d.npy"
+        nccl_id = capi.nccl_unique_id() if nranks > 1 else None
+        ctx = mp.get_context("spawn")
+        procs = [ctx.Process(target=multi_worker.run_edits, args=(r, nranks, nccl_id, out, capi.MATH_EXACT)) for r in range(nranks)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(300)
+        codes = [p.exitcode for p in procs]
+        for p in procs:
+            if p.exitcode is None:
+                p.kill(); p.join(10)
+        assert codes == [0] * nranks, codes
+        outs[nranks] = ([np.load(out % r) for r in range(nranks)], [np.load((out % r) + ".ev.npy") for r in range(nranks)])
+    one, ev1 = outs[1]
+    many, evn = outs[min(2, gpu_count())]
+    assert len(one[0]) > 1010 + 1400 and ev1[0][3] > 40
+    for r in range(len(many)):
+        assert many[r].tobytes() == one[0].tobytes()
+        assert evn[r][4] == ev1[0][4]                       # particles emitted: known on every rank
+    assert sum(e[:4] for e in evn).tolist() == ev1[0][:4].tolist()
