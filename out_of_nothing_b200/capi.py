@@ -83,7 +83,7 @@ EXPORTS = [
     "oon_synchronize", "oon_drain_events",
     "oon_timer_start", "oon_timer_stop", "oon_step_profiled", "oon_bench_frames", "oon_bench_frames_profiled", "oon_launch_count", "oon_exchange_kind",
     "oon_measure_fp32_peak", "oon_measure_copy_bandwidth",
-    "oon_debug_capture_pairs", "oon_debug_fetch_pairs", "oon_debug_fetch_kick", "oon_debug_fetch_removed", "oon_debug_time_interact",
+    "oon_debug_capture_pairs", "oon_debug_fetch_pairs", "oon_debug_fetch_kick", "oon_debug_fetch_removed", "oon_debug_time_interact", "oon_debug_trace_interact", "oon_debug_ieee_selftest",
 ]
 
 _lib = None
@@ -161,6 +161,8 @@ def load():
     L.oon_debug_fetch_kick.argtypes = [vp, vp, u64, P(u64)]
     L.oon_debug_fetch_removed.argtypes = [vp, vp, u64, P(u64)]
     L.oon_debug_time_interact.argtypes = [vp, f32, u32, u32, P(f32)]
+    L.oon_debug_ieee_selftest.argtypes = [i32, u64, u64, P(u64)]
+    L.oon_debug_trace_interact.argtypes = [vp, f32, u32, u32, vp, u64, P(u64), P(f32)]
     for name in EXPORTS:
         if name != "oon_last_error":
             getattr(L, name).restype = i32
@@ -190,6 +192,16 @@ def measure_copy_bandwidth(device: int = 0) -> float:
     L = load()
     out = ctypes.c_double()
     rc = L.oon_measure_copy_bandwidth(device, ctypes.byref(out))
+    if rc:
+        raise OonError(rc, (L.oon_last_error(None) or b"").decode())
+    return out.value
+
+
+def ieee_selftest(device: int = 0, n: int = 1 << 26, seed: int = 1) -> int:
+    """mismatches between the EXACT kernel's written-out sqrt.rn / div.rn fast paths and the intrinsics over n operand sets"""
+    L = load()
+    out = ctypes.c_uint64()
+    rc = L.oon_debug_ieee_selftest(device, n, seed, ctypes.byref(out))
     if rc:
         raise OonError(rc, (L.oon_last_error(None) or b"").decode())
     return out.value

@@ -123,6 +123,7 @@ struct oon_world {
     uint32_t group_tiles_override = 0, debug_gpc = 0, debug_spc = 0, tail_waves_x2 = 4;
     int small_tiles_override = -1;
     uint32_t dbg_fraction = 0, dbg_part = 0;             // oon_debug_time_interact: launch a part of the target blocks
+    unsigned long long* dbg_trace = nullptr; uint32_t dbg_trace_ctas = 0;   // oon_debug_trace_interact: per-CTA timeline of that launch
     float4* scratch4 = nullptr;                          // player-only reaction buffer, one float4 per slot
     size_t tiles_cap_slots = 0;                          // slots the exchange buffer (and scratch4) can hold
     float2* kick = nullptr; uint32_t kick_cap = 0; bool kick_valid = false;
@@ -748,7 +749,7 @@ int do_interact(oon_world* w, const StepParams& sp, Prof* prof) {
         if (sp.n2n)
             launched = launch_interact(w->stream, w->tiles, total_tiles(w), geo, uint32_t(w->rank) * w->block, w->block,
                                        w->d_n, w->soa[w->cur].d, uint32_t(w->rank) * w->block, sp, xv, w->acc, w->touch, w->fx_scale, w->partial,
-                                       w->counters, w->cap, w->dbg_fraction, w->dbg_part);
+                                       w->counters, w->cap, w->dbg_fraction, w->dbg_part, w->dbg_trace, &w->dbg_trace_ctas);
         else
             launched = launch_wait_peers(w->stream, xv) +
                        launch_interact_player_only(w->stream, w->tiles, total_tiles(w), uint32_t(w->rank) * w->block, w->block, w->d_n,
@@ -1025,6 +1026,25 @@ int oon_debug_time_interact(oon_world* w, float dt, uint32_t fraction, uint32_t 
     CU(w, cudaEventSynchronize(w->ev_stop));
     CU(w, cudaEventElapsedTime(ms, w->ev_start, w->ev_stop));
     return OON_OK;
+}
+
+int oon_debug_trace_interact(oon_world* w, float dt, uint32_t fraction, uint32_t part, uint64_t* trace, uint64_t capacity_ctas, uint64_t* n_ctas_out, float* ms) {
+    CHECK_W(w);
+    if (!trace || !n_ctas_out || !ms) return fail(w, OON_ERR_INVALID, "null output");
+    if (!w->kids.empty()) return fail(w, OON_ERR_UNSUPPORTED, "oon_debug_trace_interact works on a single-GPU handle");
+    unsigned long long* dev = nullptr;
+    CU(w, cudaMalloc(&dev, sizeof(unsigned long long) * 3 * size_t(capacity_ctas)));
+    CU(w, cudaMemsetAsync(dev, 0, sizeof(unsigned long long) * 3 * size_t(capacity_ctas), w->stream));
+    w->dbg_trace = dev;
+    const int rc = oon_debug_time_interact(w, dt, fraction, part, ms);
+    w->dbg_trace = nullptr;
+    *n_ctas_out = w->dbg_trace_ctas;
+    int rc2 = OON_OK;
+    if (rc == OON_OK && w->dbg_trace_ctas > capacity_ctas) rc2 = fail(w, OON_ERR_CAPACITY, "trace needs room for %u CTAs", w->dbg_trace_ctas);
+    if (rc == OON_OK && rc2 == OON_OK && cudaMemcpy(trace, dev, sizeof(unsigned long long) * 3 * size_t(w->dbg_trace_ctas), cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc2 = fail(w, OON_ERR_CUDA, "trace copy failed");
+    cudaFree(dev);
+    return rc ? rc : rc2;
 }
 
 const char* oon_last_error(const oon_world* w) { return w ? w->error.c_str() : g_create_error.c_str(); }
@@ -1548,26 +1568,41 @@ int oon_body_count(oon_world* w, uint64_t* n_out) {
 // the shard that owns the body; the bookkeeping (counts, totals, "bodies can expire") is updated identically everywhere
 // without communication.  Appends go to the tail of the table: the last non-empty rank, or the next one when that is full.
 
-// Make room for k more bodies at the tail; *append_rank_out = rank that takes them.  When neither the last non-empty rank
-// nor its successor has the room, the whole world is laid out afresh for the larger size (through the host: rare).
-static int make_room(oon_world* h, uint64_t k, int* append_rank_out) {
+// Plan where k more bodies go at the tail of the table: the free slots of the last non-empty rank, then the ranks after it
+// (`single`: all on ONE rank — the emitters append from one kernel).  When the tail has no room the whole world is laid out
+// afresh for the larger size (through the host: rare).
+struct Segment { int rank; uint32_t count; };
+static int make_room(oon_world* h, uint64_t k, bool single, std::vector<Segment>* plan) {
     Team& T = h->team;
+    plan->clear();
     int rc = team_sync_count(T);
     if (rc) return rc;
     oon_world* w0 = T[0];
+    if (k > 0x3fffffffull) return fail(h, OON_ERR_INVALID, "cannot append %llu bodies", (unsigned long long)k);
     if (w0->nranks == 1) {
         if (uint64_t(w0->n_local) + k > w0->block) {
             const uint32_t keep = w0->n_local;
             if ((rc = team_layout(T, uint64_t(keep) + k, keep, true))) return rc;
         }
-        *append_rank_out = 0;
+        plan->push_back({0, uint32_t(k)});
         return OON_OK;
     }
     for (int attempt = 0; attempt < 2; ++attempt) {
         int last = 0;
         for (int g = 0; g < w0->nranks; ++g) if (rank_count(w0, g)) last = g;
-        if (uint64_t(rank_count(w0, last)) + k <= w0->block) { *append_rank_out = last; return OON_OK; }
-        if (last + 1 < w0->nranks && k <= w0->block) { *append_rank_out = last + 1; return OON_OK; }
+        plan->clear();
+        if (single) {
+            if (uint64_t(rank_count(w0, last)) + k <= w0->block) { plan->push_back({last, uint32_t(k)}); return OON_OK; }
+            if (last + 1 < w0->nranks && k <= w0->block) { plan->push_back({last + 1, uint32_t(k)}); return OON_OK; }
+        } else {
+            uint64_t remaining = k;
+            for (int g = last; g < w0->nranks && remaining; ++g) {
+                const uint64_t take = std::min<uint64_t>(w0->block - rank_count(w0, g), remaining);
+                if (take) plan->push_back({g, uint32_t(take)});
+                remaining -= take;
+            }
+            if (!remaining) return OON_OK;
+        }
         if (attempt) break;
         // no room at the tail: gather the table on the host and lay the world out again with room for k more
         const uint64_t n = w0->n_total;
@@ -1575,7 +1610,8 @@ static int make_room(oon_world* h, uint64_t k, int* append_rank_out) {
         uint64_t got = 0;
         if ((rc = download_common(h, all.data(), n, &got))) return rc;
         const bool mortals = w0->has_mortals;
-        if ((rc = upload_common(h, all.data(), false, 0, n, n + k))) return rc;
+        const uint64_t n_cap = single ? std::max<uint64_t>(n + k, k * uint64_t(w0->nranks)) : n + k;    // single: a block must hold the burst
+        if ((rc = upload_common(h, all.data(), false, 0, n, n_cap))) return rc;
         for (oon_world* w : T) w->has_mortals = w->has_mortals || mortals;
     }
     return fail(h, OON_ERR_CAPACITY, "cannot append %llu bodies to the sharded world", (unsigned long long)k);
@@ -1600,21 +1636,25 @@ int oon_add_bodies(oon_world* h, const oon_body_f32* bodies, uint64_t k) {
     if (rc) return rc;
     if (!k) return OON_OK;
     if (!bodies) return fail(h, OON_ERR_INVALID, "null body table");
-    int arank = 0;
-    if ((rc = make_room(h, k, &arank))) return rc;
+    std::vector<Segment> plan;
+    if ((rc = make_room(h, k, false, &plan))) return rc;
     bool mortals = false;
     for (uint64_t i = 0; i < k; ++i) mortals |= mortal(bodies[i].lifetime);
-    if (oon_world* w = member_of_rank(T, arank)) {
-        USE(w);
-        if ((rc = ensure_aos(w, k))) return rc;
-        const uint32_t at = w->n_local, now = w->n_local + uint32_t(k);
-        CU(w, cudaMemcpyAsync(w->aos_dev, bodies, size_t(k) * sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
-        w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, at, uint32_t(k), nullptr);
-        CU(w, cudaGetLastError());
-        CU(w, cudaMemcpyAsync(w->d_n, &now, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
-        SYNC(w);
+    uint64_t done = 0;
+    for (const Segment& seg : plan) {                       // in order: the last non-empty rank is filled to the brim first
+        if (oon_world* w = member_of_rank(T, seg.rank)) {
+            USE(w);
+            if ((rc = ensure_aos(w, seg.count))) return rc;
+            const uint32_t at = w->n_local, now = w->n_local + seg.count;
+            CU(w, cudaMemcpyAsync(w->aos_dev, bodies + done, size_t(seg.count) * sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
+            w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, at, seg.count, nullptr);
+            CU(w, cudaGetLastError());
+            CU(w, cudaMemcpyAsync(w->d_n, &now, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
+            SYNC(w);
+        }
+        note_append(T, seg.rank, seg.count, mortals);
+        done += seg.count;
     }
-    note_append(T, arank, k, mortals);
     return OON_OK;
 }
 
@@ -1648,8 +1688,9 @@ static int emit_common(oon_world* h, int kind, uint64_t base_ndx, uint64_t paren
     if (base_ndx >= w0->n_total || parent_ndx >= w0->n_total)
         return fail(h, OON_ERR_INVALID, "%s: body index %llu out of range (%llu bodies)", what, (unsigned long long)std::max(base_ndx, parent_ndx), (unsigned long long)w0->n_total);
     if (!n) return OON_OK;
-    int arank = 0;
-    if ((rc = make_room(h, n, &arank))) return rc;         // room for all n; the counts are corrected below
+    std::vector<Segment> plan;
+    if ((rc = make_room(h, n, true, &plan))) return rc;    // room for all n on one rank; the counts are corrected below
+    const int arank = plan[0].rank;
     uint32_t elocal = 0, plocal = 0;
     const int erank = owner_of(w0, base_ndx, &elocal), prank = owner_of(w0, parent_ndx, &plocal);
     const bool sharded = w0->nranks > 1;
@@ -2018,6 +2059,20 @@ int oon_measure_copy_bandwidth(int device, double* gbs_out) {
     const float g = measure_copy_gbs(nullptr);
     if (g <= 0) return fail(nullptr, OON_ERR_CUDA, "copy probe failed");
     *gbs_out = g;
+    return OON_OK;
+}
+
+int oon_debug_ieee_selftest(int device, uint64_t n, uint64_t seed, uint64_t* mismatches_out) {
+    if (!mismatches_out) return OON_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return fail(nullptr, OON_ERR_NO_DEVICE, "cudaSetDevice(%d) failed", device); }
+    unsigned long long* d = nullptr;
+    unsigned long long h = 0;
+    if (cudaMalloc(&d, sizeof h) != cudaSuccess || cudaMemset(d, 0, sizeof h) != cudaSuccess) return fail(nullptr, OON_ERR_CUDA, "selftest allocation failed");
+    run_ieee_selftest(nullptr, n, seed, d);
+    const cudaError_t e = cudaMemcpy(&h, d, sizeof h, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(nullptr, OON_ERR_CUDA, "selftest failed: %s", cudaGetErrorString(e));
+    *mismatches_out = h;
     return OON_OK;
 }
 

@@ -179,7 +179,8 @@ struct InteractGeometry {
 int launch_interact(cudaStream_t st, const float* tiles, uint32_t ntiles, const InteractGeometry& geo,
                     uint32_t target_base, uint32_t slots, const uint32_t* d_n_local, BodySoA soa, uint32_t body_base,
                     StepParams sp, const ExchangeView& xv, unsigned long long* acc, uint32_t* touch, int* fx_scale, float4* partial,
-                    unsigned long long* counters, CaptureBuf cap, uint32_t dbg_fraction = 0, uint32_t dbg_part = 0);
+                    unsigned long long* counters, CaptureBuf cap, uint32_t dbg_fraction = 0, uint32_t dbg_part = 0,
+                    unsigned long long* trace = nullptr /* tuning aid: 3 words per CTA */, uint32_t* trace_ctas = nullptr);
 // Peer-to-peer exchange: hold the stream until every peer's slice of epoch xv.epoch has landed (for the kernels that
 // read the exchange buffer without waiting themselves).
 int launch_wait_peers(cudaStream_t st, const ExchangeView& xv);
@@ -214,6 +215,9 @@ int launch_sweep_compact(cudaStream_t st, BodySoA src, BodySoA dst, uint32_t* d_
 
 // render read set: {x, y, r} per body + the colour word
 int launch_render_pack(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint32_t slots, float* xyr, uint32_t* colors);
+
+// self-test of the EXACT kernel's written-out IEEE sqrt / division fast paths against the intrinsics (n random operand sets)
+int run_ieee_selftest(cudaStream_t st, unsigned long long n, unsigned long long seed, unsigned long long* d_mismatches);
 
 // microbenchmarks
 float measure_fp32_peak_tflops(cudaStream_t st);

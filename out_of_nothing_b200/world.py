@@ -344,6 +344,13 @@ class World:
         self._check(self._L.oon_debug_time_interact(self._h, dt, fraction, part, ctypes.byref(ms)))
         return ms.value
 
+    def debug_trace_interact(self, dt: float, fraction: int, part: int = 0, capacity: int = 1 << 16):
+        """-> (ms, trace[n_ctas, 3] = {SM id | tiles << 32, start ns, end ns}) of the launch debug_time_interact times."""
+        out = np.zeros((capacity, 3), np.uint64)
+        n, ms = ctypes.c_uint64(), ctypes.c_float()
+        self._check(self._L.oon_debug_trace_interact(self._h, dt, fraction, part, out.ctypes.data, capacity, ctypes.byref(n), ctypes.byref(ms)))
+        return ms.value, out[: n.value]
+
     def launch_count(self) -> int:
         n = ctypes.c_uint64()
         self._check(self._L.oon_launch_count(self._h, ctypes.byref(n)))

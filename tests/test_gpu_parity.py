@@ -647,6 +647,13 @@ def test_extreme_mass_ratio_keeps_the_small_kicks():
     assert e0 <= 10 * TOL_KICK_MAX, e0
 
 
+def test_written_out_ieee_fast_paths_equal_the_intrinsics():
+    """k_interact_exact's sqrt.rn / div.rn sequences (shared reciprocal, guards taken together) vs __fsqrt_rn / __fdiv_rn:
+    2 x 2^27 random and edge-case operand sets over the whole validity window, bit for bit."""
+    assert capi.ieee_selftest(0, 1 << 27, seed=1) == 0
+    assert capi.ieee_selftest(0, 1 << 27, seed=0xC0FFEE) == 0
+
+
 # ---------------------------------------------------------------------------------------------- render sync (row f4)
 def test_render_readback_runs_beside_the_next_frames(kat1):
     """oon_download_render_begin/_end: the positions of frame k reach pinned host memory while frames k+1.. are computed."""
