@@ -10,6 +10,7 @@
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost nothing unless a tool (nsys, ncu --nvtx) is attached
 
 #include <algorithm>
+#include <functional>
 #include <utility>
 #include <cmath>
 #include <cstdarg>
@@ -94,6 +95,13 @@ struct oon_world {
     uint32_t cblock = 0;      // bodies per canonical block (block == cblock * 8 / nranks)
     uint32_t n_local = 0;     // host view of the live local count
     bool counts_stale = false; // a sweep ran on the device since the host last learnt the counts
+    // What the host knows about expiry (same on every shard): while `life_known`, no body is expired and none can expire
+    // before `life_budget` more seconds of dt have passed — such frames run the immortal schedule (no sweep, fused launches,
+    // Hilbert order).  Learnt from the device at uploads and whenever the counts are fetched after a sweep; kept by edits.
+    bool life_known = false, pending_expired = false;
+    double life_budget = 0.0;
+    bool last_frame_swept = false; // the most recent frame ended with a sweep (oon_debug_fetch_removed: else nothing was removed)
+    uint32_t* d_minfo = nullptr;   // [4] lifetime summary written by the unpack / sweep kernels (see note_lifetime)
     bool has_mortals = false; // any body with lifetime > 0 or a non-unlimited non-positive lifetime
     uint32_t player_ndx = 0;  // player_entity_ndx(): the sweep inside oon_step tests the bodies after it (OON.cpp:1089)
 
@@ -147,6 +155,8 @@ struct oon_world {
     // slot order of the exchange buffer: inv[slot] = local body stored there
     uint32_t* inv = nullptr; uint32_t inv_cap = 0;
     uint32_t* inv_next = nullptr;   // order being computed ahead on the aux stream (from the positions of the current frame)
+    uint32_t* slot_of = nullptr;    // [body] slot it was packed into (inverse of inv as of the last pack)
+    bool fuse_reorder = true;       // integrate(k) + pack(k+1) in one launch even when the slot order changes in between
     cudaStream_t aux = nullptr;     // sort-ahead stream: the O(N) ordering of frame k+1 hides behind the O(N^2) pass of frame k
     cudaEvent_t ev_main = nullptr, ev_sorted = nullptr;
     bool next_order_pending = false;
@@ -405,10 +415,11 @@ int layout_one(oon_world* w, uint64_t n_cap, uint64_t n_present, uint32_t keep, 
     }
     if (w->soa[w->cur].cap > w->inv_cap) {
         if (w->next_order_pending) { CU(w, cudaStreamSynchronize(w->aux)); w->next_order_pending = false; }
-        cudaFree(w->inv); cudaFree(w->inv_next); w->inv = nullptr; w->inv_next = nullptr; w->inv_cap = 0;
+        cudaFree(w->inv); cudaFree(w->inv_next); cudaFree(w->slot_of); w->inv = nullptr; w->inv_next = nullptr; w->slot_of = nullptr; w->inv_cap = 0;
         int rc = dev_alloc(w, &w->inv, w->soa[w->cur].cap);
         if (rc) return rc;
         if ((rc = dev_alloc(w, &w->inv_next, w->soa[w->cur].cap))) return rc;
+        if ((rc = dev_alloc(w, &w->slot_of, w->soa[w->cur].cap))) return rc;
         w->inv_cap = w->soa[w->cur].cap;
     }
     if (block != w->block || n_present != w->n_total) {   // same table shape: a stale order is still a valid (if less tight) order
@@ -619,8 +630,9 @@ int exchange(oon_world* w, Prof* prof) {
 // Space-filling-curve order pays through box culling once the O(N^2) pass dwarfs the O(N) sort (a re-sort costs
 // ~0.1 ms; bodies of these worlds cross a tile's width in a few frames, so the order is refreshed every
 // `resort_every` frames, default 1).  Small worlds and worlds with mortal bodies keep the identity order.
+bool mortal_frame(const oon_world* w, float dt);
 bool wants_morton(const oon_world* w, const StepParams& sp) {
-    return sp.n2n && !sp.exact && !w->has_mortals && w->morton_enabled && w->n_total >= w->morton_min_bodies;
+    return sp.n2n && !sp.exact && !mortal_frame(w, sp.dt) && w->morton_enabled && w->n_total >= w->morton_min_bodies;
 }
 
 // Make inv[] valid for the coming pack: identity for the reference-order kernels, Morton order of the current
@@ -719,7 +731,7 @@ int do_intrinsic_pack(oon_world* w, const StepParams& sp, bool intrinsic, Prof* 
     PackOut out;
     if ((rc = begin_pack(w, out))) return rc;
     rc = timed(w, prof, 1, [&](int& launched) -> int {
-        launched = launch_intrinsic_pack(w->stream, w->soa[w->cur].d, w->inv, w->d_n, w->block, uint32_t(w->rank) * w->block,
+        launched = launch_intrinsic_pack(w->stream, w->soa[w->cur].d, w->inv, w->slot_of, w->d_n, w->block, uint32_t(w->rank) * w->block,
                                          out, sp, intrinsic, w->counters);
         CU(w, cudaGetLastError());
         return OON_OK;
@@ -777,6 +789,11 @@ int ensure_kick(oon_world* w, const StepParams& sp) {
     return OON_OK;
 }
 
+// An order computed ahead is waiting and this integrate may pack the next frame in it (see do_integrate).
+bool can_fuse_reorder(const oon_world* w, const StepParams& sp) {
+    return w->fuse_reorder && w->async_sort && w->resort_every == 1 && wants_morton(w, sp) && w->order_kind == 2 && !w->order_dirty && w->next_order_pending;
+}
+
 int do_integrate(oon_world* w, const StepParams& sp, bool apply_pairwise, bool do_global, bool fuse_next, Prof* prof) {
     NvtxRange range(fuse_next ? "oon/integrate+pack" : "oon/integrate");
     int rc = ensure_kick(w, sp);
@@ -784,12 +801,22 @@ int do_integrate(oon_world* w, const StepParams& sp, bool apply_pairwise, bool d
     if ((rc = ensure_order(w, sp, prof, false))) return rc;
     if (w->next_order_pending && (do_global || apply_pairwise))       // the sort-ahead reads the positions this kernel rewrites
         CU(w, cudaStreamWaitEvent(w->stream, w->ev_sorted, 0));
+    // Large FAST worlds re-order their slots every frame (the order of frame k+1 is computed beside frame k's interact
+    // kernel).  The fused kernel then packs frame k+1 in the NEW order while it integrates frame k: it runs over the new
+    // slots and finds the sums of the body it meets at the slot that body had during the pass (slot_of[], kept by the packs).
+    bool reorder = false;
+    if (fuse_next && apply_pairwise && can_fuse_reorder(w, sp)) {
+        std::swap(w->inv, w->inv_next);
+        w->next_order_pending = false;
+        w->order_age = 0;
+        reorder = true;
+    }
     PackOut out{};
     if (fuse_next && (rc = begin_pack(w, out))) return rc;
     rc = timed(w, prof, 1, [&](int& launched) -> int {
         launched = launch_integrate(w->stream, w->soa[w->cur].d, w->inv, w->d_n, w->block, uint32_t(w->rank) * w->block, w->partial,
                                     w->acc, w->touch, w->fx_scale, sp, apply_pairwise, do_global, fuse_next, out,
-                                    (apply_pairwise && wants_kick(w, sp)) ? w->kick : nullptr, w->counters);
+                                    (apply_pairwise && wants_kick(w, sp)) ? w->kick : nullptr, w->counters, w->slot_of, reorder);
         CU(w, cudaGetLastError());
         return OON_OK;
     });
@@ -798,6 +825,8 @@ int do_integrate(oon_world* w, const StepParams& sp, bool apply_pairwise, bool d
     if (apply_pairwise && sp.n2n && !sp.exact) w->acc_dirty = false;     // k_integrate has zeroed what it read
     if (do_global || apply_pairwise) w->tiles_fresh = false;
     if (fuse_next) { rc = exchange(w, prof); if (rc) return rc; w->tiles_fresh = true; }
+    // the order of the frame after the one just packed: beside the coming interact kernel, from the state this kernel left
+    if (reorder && (rc = start_order_ahead(w, sp))) return rc;
     return OON_OK;
 }
 
@@ -881,10 +910,11 @@ int team_sweep(Team& T, uint32_t player_ndx, std::vector<Prof>* profs) {
         oon_world* w = T[i];
         USE(w);
         rc = timed(w, profs ? &(*profs)[i] : nullptr, 3, [&](int& launched) -> int {
+            CU(w, cudaMemsetAsync(w->d_minfo, 0, 4 * sizeof(uint32_t), w->stream));
             launched = (w->nranks > 1 ? 1 : 0) +
                        launch_sweep_compact(w->stream, w->soa[w->cur].d, w->soa[w->cur ^ 1].d, w->d_n, w->block, w->nranks > 1 ? w->runinfo : nullptr, w->rank,
                                             w->sweep_temp, w->sweep_temp_bytes, w->sweep_scratch, w->removed_idx, w->removed_cap,
-                                            w->d_removed_count, w->counters);
+                                            w->d_removed_count, w->counters, w->d_minfo);
             CU(w, cudaGetLastError());
             return OON_OK;
         });
@@ -893,8 +923,44 @@ int team_sweep(Team& T, uint32_t player_ndx, std::vector<Prof>* profs) {
         w->tiles_fresh = false;
         w->order_dirty = true;          // indices shifted
         w->counts_stale = true;
+        w->life_known = false;          // until the next fetch of the counts brings the survivors' summary
     }
     return OON_OK;
+}
+
+bool mortal(float lifetime) { return lifetime > 0.f || (lifetime != LIFETIME_UNLIMITED && lifetime <= 0.f); }
+
+// Take the lifetime summaries of all shards (3 words each, see note_lifetime) into the host's schedule state.
+void apply_lifetime_info(Team& T, const std::vector<uint32_t>& info /* [nranks][4]: {-, any, pending, ~min bits} */) {
+    bool any = false, pending = false;
+    double budget = 1e300;
+    for (size_t r = 0; r * 4 + 3 < info.size() + 0; ++r) {
+        any = any || info[4 * r + 1] != 0;
+        pending = pending || info[4 * r + 2] != 0;
+        if (info[4 * r + 3]) { const uint32_t bits = ~info[4 * r + 3]; float f; std::memcpy(&f, &bits, sizeof f); budget = std::min(budget, double(f)); }
+    }
+    for (oon_world* w : T) {
+        w->has_mortals = any;
+        w->life_known = true;
+        w->pending_expired = pending;
+        w->life_budget = budget;
+    }
+}
+// A body with this lifetime entered the table through the host (add / set / emit): keep the schedule state conservative.
+void note_host_lifetime(Team& T, float life) {
+    if (!mortal(life)) return;
+    for (oon_world* w : T) {
+        w->has_mortals = true;
+        if (life > 0.f) w->life_budget = std::min(w->life_budget, double(life)); else w->pending_expired = true;
+    }
+}
+// Does the coming frame need the mortal schedule (sweep, no fusion, identity order)?  Not while the host KNOWS that nothing is
+// expired and nothing can expire within this frame and the next (two frames of margin cover the rounding of the device's
+// frame-by-frame countdown against the host's running sum).
+bool mortal_frame(const oon_world* w, float dt) {
+    if (!w->has_mortals) return false;
+    if (!w->life_known || w->pending_expired) return true;
+    return !(w->life_budget > 3.0 * std::fabs(double(dt)) + 1e-6);
 }
 
 // Refresh the host's idea of the body counts after device-side removals (sweeps).
@@ -903,33 +969,31 @@ int team_sync_count(Team& T) {
     for (oon_world* w : T) stale = stale || w->counts_stale;
     if (!stale) return OON_OK;
     oon_world* w0 = T[0];
-    if (w0->nranks == 1) {
-        uint32_t n = 0;
-        CU(w0, cudaMemcpyAsync(&n, w0->d_n, sizeof n, cudaMemcpyDeviceToHost, w0->stream));
-        SYNC(w0);
-        w0->n_local = n;
-        w0->n_total = n;
-        w0->counts_stale = false;
-        return OON_OK;
-    }
-    std::vector<uint32_t> counts(size_t(w0->nranks), 0u);
-    if (T.size() > 1) {                                     // group: the host reads every shard's count itself
-        for (oon_world* w : T) { USE(w); CU(w, cudaMemcpyAsync(&counts[size_t(w->rank)], w->d_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream)); }
+    std::vector<uint32_t> info(size_t(w0->nranks) * 4, 0u);       // per rank {bodies, any mortal, expired pending, ~min positive lifetime}
+    if (T.size() > 1 || w0->nranks == 1) {                        // one GPU / group: the host reads every shard's words itself
+        for (oon_world* w : T) {
+            USE(w);
+            CU(w, cudaMemcpyAsync(&info[4 * size_t(w->rank)], w->d_n, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+            CU(w, cudaMemcpyAsync(&info[4 * size_t(w->rank) + 1], w->d_minfo, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+        }
         for (oon_world* w : T) { USE(w); SYNC(w); }
-    } else {                                                // one rank of a multi-process world: everybody learns everybody's count
-        CU(w0, cudaMemcpyAsync(w0->d_counts + w0->rank, w0->d_n, sizeof(uint32_t), cudaMemcpyDeviceToDevice, w0->stream));
-        NC(w0, g_nccl.AllGather(w0->d_counts + w0->rank, w0->d_counts, 1, ncclUint32, w0->comm, w0->stream));
-        CU(w0, cudaMemcpyAsync(counts.data(), w0->d_counts, sizeof(uint32_t) * counts.size(), cudaMemcpyDeviceToHost, w0->stream));
+    } else {                                                // one rank of a multi-process world: everybody learns everybody's
+        uint32_t* mine = w0->d_counts + 4 * w0->rank;
+        CU(w0, cudaMemcpyAsync(mine, w0->d_n, sizeof(uint32_t), cudaMemcpyDeviceToDevice, w0->stream));
+        CU(w0, cudaMemcpyAsync(mine + 1, w0->d_minfo, 3 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, w0->stream));
+        NC(w0, g_nccl.AllGather(mine, w0->d_counts, 4, ncclUint32, w0->comm, w0->stream));
+        CU(w0, cudaMemcpyAsync(info.data(), w0->d_counts, sizeof(uint32_t) * info.size(), cudaMemcpyDeviceToHost, w0->stream));
         SYNC(w0);
     }
     uint64_t total = 0;
-    for (uint32_t c : counts) total += c;
+    for (int g = 0; g < w0->nranks; ++g) total += info[4 * size_t(g)];
     for (oon_world* w : T) {
-        w->counts = counts;
-        w->n_local = counts[size_t(w->rank)];
+        if (w->nranks > 1) for (int g = 0; g < w->nranks; ++g) w->counts[size_t(g)] = info[4 * size_t(g)];
+        w->n_local = info[4 * size_t(w->rank)];
         w->n_total = total;
         w->counts_stale = false;
     }
+    apply_lifetime_info(T, info);                           // the summaries describe the survivors of the last sweep == the table as it is
     return OON_OK;
 }
 
@@ -940,27 +1004,37 @@ uint64_t rank_first(const oon_world* w, int g) { uint64_t f = 0; for (int h = 0;
 // nsteps frames for every shard of the team, phase by phase: all packs are enqueued before the first interact kernel that
 // waits for them (a group's shards wait for each other's flags ON THE DEVICE; the single host thread must never block on a
 // kernel whose peers' producers it has not enqueued yet).
-int team_step(Team& T, float dt, uint32_t nsteps, std::vector<Prof>* profs) {
+// hook (optional): called with (frame, 0) before the first kernel that belongs to a frame alone and (frame, 1) after its
+// last one — the benchmark's per-frame L2 flush and event pairs.  A frame's kernels: [intrinsic+pack unless the previous
+// frame's integrate packed it] -> interact -> integrate (+ the next frame's intrinsic+pack when fused) [-> sweep].
+typedef std::function<int(uint32_t, int)> FrameHook;
+int team_step(Team& T, float dt, uint32_t nsteps, std::vector<Prof>* profs, const FrameHook* hook = nullptr) {
     NvtxRange range("oon/step");
     oon_world* w0 = T[0];
     if (!nsteps || !w0->block) { for (oon_world* w : T) w->steps += nsteps; return OON_OK; }
     const StepParams sp = step_params(w0, dt);
-    const bool sweep = w0->has_mortals;
     auto prof_of = [&](size_t i) { return profs ? &(*profs)[i] : nullptr; };
     int rc;
-    // Frame k: intrinsic+pack -> (exchange) -> interact -> integrate.  Without mortal bodies the integrate kernel of
-    // frame k also runs frame k+1's intrinsic+pack (one pass over the SoA, one launch) unless the slot order is due
-    // for a refresh.
-    for (size_t i = 0; i < T.size(); ++i) { USE(T[i]); if ((rc = do_intrinsic_pack(T[i], sp, true, prof_of(i)))) return rc; }
+    bool packed = false;                                   // the coming frame's tiles were packed by the previous integrate
     for (uint32_t k = 0; k < nsteps; ++k) {
+        // Bodies that can expire bring the sweep, and with it the plain schedule — but only on frames where the host cannot
+        // rule an expiry out (mortal_frame); a world whose mortals are all far from their end runs like an immortal one.
+        const bool sweep = mortal_frame(w0, dt);
+        if (hook && (rc = (*hook)(k, 0))) return rc;
+        if (!packed)
+            for (size_t i = 0; i < T.size(); ++i) { USE(T[i]); if ((rc = do_intrinsic_pack(T[i], sp, true, prof_of(i)))) return rc; }
         for (size_t i = 0; i < T.size(); ++i) { USE(T[i]); if ((rc = do_interact(T[i], sp, prof_of(i)))) return rc; ++T[i]->order_age; }
         const bool last = k + 1 == nsteps;
+        // Without mortal bodies the integrate kernel of frame k also runs frame k+1's intrinsic+pack (one pass over the SoA,
+        // one launch) — in the next frame's slot order when that is being refreshed every frame and is ready (do_integrate).
         const bool resort_due = wants_morton(w0, sp) && (w0->order_age >= w0->resort_every || w0->next_order_pending);
-        const bool fuse = !sweep && !last && !resort_due;
+        const bool fuse = !sweep && !last && (!resort_due || can_fuse_reorder(w0, sp));      // (mortal_frame's margin covers the next frame's intrinsic too)
         for (size_t i = 0; i < T.size(); ++i) { USE(T[i]); if ((rc = do_integrate(T[i], sp, true, true, fuse, prof_of(i)))) return rc; }
         if (sweep && (rc = team_sweep(T, w0->player_ndx, profs))) return rc;
-        if (!fuse && !last)
-            for (size_t i = 0; i < T.size(); ++i) { USE(T[i]); if ((rc = do_intrinsic_pack(T[i], sp, true, prof_of(i)))) return rc; }
+        for (oon_world* w : T) w->last_frame_swept = sweep;
+        for (oon_world* w : T) if (w->life_known) w->life_budget -= double(dt);      // the intrinsic pass counted every lifetime down by dt
+        packed = fuse;
+        if (hook && (rc = (*hook)(k, 1))) return rc;
     }
     for (oon_world* w : T) w->steps += nsteps;
     return OON_OK;
@@ -979,8 +1053,6 @@ int team_sync(Team& T) {
     for (oon_world* w : T) { USE(w); SYNC(w); }
     return OON_OK;
 }
-
-bool mortal(float lifetime) { return lifetime > 0.f || (lifetime != LIFETIME_UNLIMITED && lifetime <= 0.f); }
 
 // Which shard of the team (index into T, -1: none of mine) owns global body `ndx`, and where it sits there.
 // Needs fresh counts (team_sync_count).
@@ -1104,6 +1176,7 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
     if (const char* e = getenv("OON_ORDER_ONE_CTA")) w->order_one_cta = atoi(e) != 0;
     if (const char* e = getenv("OON_MORTON_MIN")) { long v = atol(e); if (v >= 0) w->morton_min_bodies = uint64_t(v); }
     if (const char* e = getenv("OON_RESORT_EVERY")) { long v = atol(e); if (v > 0) w->resort_every = uint32_t(v); }
+    if (const char* e = getenv("OON_FUSE_REORDER")) w->fuse_reorder = atoi(e) != 0;
     auto bail = [&](int code) { std::string msg = w->error; oon_destroy(w); g_create_error = msg; return code; };
 #define CUB_(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { w->error = std::string(#call) + " failed: " + cudaGetErrorString(e_); return bail(OON_ERR_CUDA); } } while (0)
     CUB_(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
@@ -1121,6 +1194,7 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
     CUB_(cudaMalloc(&w->counters, sizeof(unsigned long long) * C_COUNT));
     CUB_(cudaMemset(w->counters, 0, sizeof(unsigned long long) * C_COUNT));
     CUB_(cudaMalloc(&w->fx_scale, sizeof(int))); CUB_(cudaMemset(w->fx_scale, 0, sizeof(int)));
+    CUB_(cudaMalloc(&w->d_minfo, 4 * sizeof(uint32_t))); CUB_(cudaMemset(w->d_minfo, 0, 4 * sizeof(uint32_t)));
     CUB_(cudaMalloc(&w->emit_rec, sizeof(EmitBase) * size_t(nranks))); CUB_(cudaMemset(w->emit_rec, 0, sizeof(EmitBase) * size_t(nranks)));
     {
         const uint32_t init[3] = {0u, 0x7f61b1e6u /* BOX_EMPTY */, 0u};
@@ -1134,7 +1208,7 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
         CUB_(cudaHostGetDevicePointer(reinterpret_cast<void**>(&w->timeouts), w->timeouts_host, 0));
         CUB_(cudaMalloc(&w->ipc_stage, 256 * size_t(nranks)));
         CUB_(cudaMalloc(&w->runinfo, sizeof(int) * 4 * size_t(nranks))); CUB_(cudaMemset(w->runinfo, 0, sizeof(int) * 4 * size_t(nranks)));
-        CUB_(cudaMalloc(&w->d_counts, sizeof(uint32_t) * size_t(nranks)));
+        CUB_(cudaMalloc(&w->d_counts, sizeof(uint32_t) * 4 * size_t(nranks)));     // per rank {bodies, lifetime summary[3]}
         w->counts.assign(size_t(nranks), 0u);
     }
 #undef CUB_
@@ -1217,13 +1291,13 @@ int oon_destroy(oon_world* w) {
     if (w->ev_sorted) cudaEventDestroy(w->ev_sorted);
     if (w->ev_grp) cudaEventDestroy(w->ev_grp);
     if (w->ev_grp_done) cudaEventDestroy(w->ev_grp_done);
-    cudaFree(w->inv_next);
+    cudaFree(w->inv_next); cudaFree(w->slot_of);
     if (w->copy_stream) { cudaStreamSynchronize(w->copy_stream); cudaStreamDestroy(w->copy_stream); cudaEventDestroy(w->ev_render_ready); cudaEventDestroy(w->ev_render_done); }
     if (w->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(w->comm);
     soa_free(w->soa[0]); soa_free(w->soa[1]);
     cudaFree(w->tiles_buf[0]); cudaFree(w->tiles_buf[1]); cudaFree(w->acc); cudaFree(w->touch); cudaFree(w->fx_scale); cudaFree(w->rank_stats);
     cudaFree(w->flags); if (w->timeouts_host) cudaFreeHost(w->timeouts_host); cudaFree(w->ipc_stage); cudaFree(w->runinfo); cudaFree(w->d_counts); cudaFree(w->partial); cudaFree(w->scratch4); cudaFree(w->kick); cudaFree(w->d_n); cudaFree(w->d_removed_count);
-    cudaFree(w->counters); cudaFree(w->sweep_temp); cudaFree(w->sweep_scratch); cudaFree(w->removed_idx); cudaFree(w->aos_dev); cudaFree(w->emit_rec);
+    cudaFree(w->counters); cudaFree(w->sweep_temp); cudaFree(w->sweep_scratch); cudaFree(w->removed_idx); cudaFree(w->aos_dev); cudaFree(w->emit_rec); cudaFree(w->d_minfo);
     cudaFree(w->xyr_dev); cudaFree(w->cap.coll); cudaFree(w->cap.touch);
     cudaFree(w->inv); cudaFree(w->order_temp); cudaFree(w->order_keys); cudaFree(w->order_vals); cudaFree(w->order_bounds);
     if (w->ev_start) cudaEventDestroy(w->ev_start);
@@ -1297,31 +1371,29 @@ static int upload_common(oon_world* h, const oon_body_f32* src, bool is_block, u
             return fail(w, OON_ERR_INVALID, "upload_local: rank %d of %d owns %u bodies of a %llu-body world (from index %llu), got %llu",
                         w->rank, w->nranks, w->n_local, (unsigned long long)n, (unsigned long long)lo, (unsigned long long)count);
         const oon_body_f32* mine = is_block ? src : src + lo;
-        CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));     // doubles as the unpack kernel's "mortal seen" flag
+        CU(w, cudaMemsetAsync(w->d_minfo, 0, 4 * sizeof(uint32_t), w->stream));         // lifetime summary of the table, filled by the unpack kernel
         if (w->n_local) {
             if ((rc = ensure_aos(w, w->n_local))) return rc;
             CU(w, cudaMemcpyAsync(w->aos_dev, mine, size_t(w->n_local) * sizeof(oon_body_f32), cudaMemcpyHostToDevice, w->stream));
-            w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, 0, w->n_local, w->d_removed_count);
+            w->launches += launch_unpack_f32(w->stream, w->aos_dev, w->soa[w->cur].d, 0, w->n_local, w->d_minfo);
             CU(w, cudaGetLastError());
         }
         CU(w, cudaMemcpyAsync(w->d_n, &w->n_local, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
     }
-    std::vector<uint32_t> seen(size_t(T[0]->nranks), 0u);
+    std::vector<uint32_t> info(size_t(T[0]->nranks) * 4, 0u);      // per rank {-, any mortal, expired pending, ~min positive lifetime}
     for (oon_world* w : T) {
         USE(w);
         if (T.size() == 1 && w->nranks > 1) {
-            CU(w, cudaMemcpyAsync(w->d_counts + w->rank, w->d_removed_count, sizeof(uint32_t), cudaMemcpyDeviceToDevice, w->stream));
-            NC(w, g_nccl.AllGather(w->d_counts + w->rank, w->d_counts, 1, ncclUint32, w->comm, w->stream));
-            CU(w, cudaMemcpyAsync(seen.data(), w->d_counts, sizeof(uint32_t) * seen.size(), cudaMemcpyDeviceToHost, w->stream));
+            uint32_t* mine = w->d_counts + 4 * w->rank;
+            CU(w, cudaMemcpyAsync(mine + 1, w->d_minfo, 3 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, w->stream));
+            NC(w, g_nccl.AllGather(mine, w->d_counts, 4, ncclUint32, w->comm, w->stream));
+            CU(w, cudaMemcpyAsync(info.data(), w->d_counts, sizeof(uint32_t) * info.size(), cudaMemcpyDeviceToHost, w->stream));
         } else {
-            CU(w, cudaMemcpyAsync(&seen[size_t(w->rank)], w->d_removed_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
+            CU(w, cudaMemcpyAsync(&info[4 * size_t(w->rank) + 1], w->d_minfo, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, w->stream));
         }
-        CU(w, cudaMemsetAsync(w->d_removed_count, 0, sizeof(uint32_t), w->stream));
     }
     if ((rc = team_sync(T))) return rc;                    // the caller may reuse the host table immediately (pageable memory)
-    uint32_t any = 0;
-    for (uint32_t v : seen) any |= v;
-    for (oon_world* w : T) w->has_mortals = any != 0;
+    apply_lifetime_info(T, info);
     return OON_OK;
 }
 
@@ -1609,20 +1681,17 @@ static int make_room(oon_world* h, uint64_t k, bool single, std::vector<Segment>
         std::vector<oon_body_f32> all(n);
         uint64_t got = 0;
         if ((rc = download_common(h, all.data(), n, &got))) return rc;
-        const bool mortals = w0->has_mortals;
         const uint64_t n_cap = single ? std::max<uint64_t>(n + k, k * uint64_t(w0->nranks)) : n + k;    // single: a block must hold the burst
-        if ((rc = upload_common(h, all.data(), false, 0, n, n_cap))) return rc;
-        for (oon_world* w : T) w->has_mortals = w->has_mortals || mortals;
+        if ((rc = upload_common(h, all.data(), false, 0, n, n_cap))) return rc;     // (the lifetime summary is rebuilt from the table itself)
     }
     return fail(h, OON_ERR_CAPACITY, "cannot append %llu bodies to the sharded world", (unsigned long long)k);
 }
 
-static void note_append(Team& T, int rank, uint64_t k, bool mortals) {
+static void note_append(Team& T, int rank, uint64_t k) {
     for (oon_world* w : T) {
         if (w->nranks > 1) w->counts[size_t(rank)] += uint32_t(k);
         if (w->rank == rank) w->n_local += uint32_t(k);
         w->n_total += k;
-        w->has_mortals = w->has_mortals || mortals;
         w->tiles_fresh = false;
         w->order_dirty = true;                             // the slot order does not know the new bodies
         w->kick_valid = false;
@@ -1638,8 +1707,7 @@ int oon_add_bodies(oon_world* h, const oon_body_f32* bodies, uint64_t k) {
     if (!bodies) return fail(h, OON_ERR_INVALID, "null body table");
     std::vector<Segment> plan;
     if ((rc = make_room(h, k, false, &plan))) return rc;
-    bool mortals = false;
-    for (uint64_t i = 0; i < k; ++i) mortals |= mortal(bodies[i].lifetime);
+    for (uint64_t i = 0; i < k; ++i) note_host_lifetime(T, bodies[i].lifetime);
     uint64_t done = 0;
     for (const Segment& seg : plan) {                       // in order: the last non-empty rank is filled to the brim first
         if (oon_world* w = member_of_rank(T, seg.rank)) {
@@ -1652,7 +1720,7 @@ int oon_add_bodies(oon_world* h, const oon_body_f32* bodies, uint64_t k) {
             CU(w, cudaMemcpyAsync(w->d_n, &now, sizeof(uint32_t), cudaMemcpyHostToDevice, w->stream));
             SYNC(w);
         }
-        note_append(T, seg.rank, seg.count, mortals);
+        note_append(T, seg.rank, seg.count);
         done += seg.count;
     }
     return OON_OK;
@@ -1728,7 +1796,8 @@ static int emit_common(oon_world* h, int kind, uint64_t base_ndx, uint64_t paren
         CU(w, cudaMemcpyAsync(&res, w->emit_rec + arank, sizeof res, cudaMemcpyDeviceToHost, w->stream));
     }
     if ((rc = team_sync(T))) return rc;
-    note_append(T, arank, res.emitted, res.emitted && kind != EMIT_SPAWN && mortal(cfg->particle_lifetime));
+    note_append(T, arank, res.emitted);
+    if (res.emitted && kind != EMIT_SPAWN) note_host_lifetime(T, cfg->particle_lifetime);
     if (emitted_out) *emitted_out = res.emitted;
     return OON_OK;
 }
@@ -1800,7 +1869,8 @@ int oon_set_body(oon_world* h, uint64_t ndx, const oon_body_f32* in) {
         CU(w, cudaGetLastError());
         SYNC(w);
     }
-    for (oon_world* w : T) { w->has_mortals = w->has_mortals || mortal(in->lifetime); w->tiles_fresh = false; }
+    note_host_lifetime(T, in->lifetime);
+    for (oon_world* w : T) w->tiles_fresh = false;
     return OON_OK;
 }
 
@@ -1875,6 +1945,7 @@ int oon_update_intrinsic(oon_world* h, float dt) {
     Team& T = h->team;
     if (!T[0]->block) return OON_OK;
     for (oon_world* w : T) { USE(w); int rc = do_intrinsic_pack(w, step_params(w, dt), true, nullptr); if (rc) return rc; }
+    for (oon_world* w : T) if (w->life_known) w->life_budget -= double(dt);          // every lifetime was counted down by dt
     return OON_OK;
 }
 
@@ -1901,7 +1972,9 @@ int oon_update_global(oon_world* h, float dt) {
 int oon_sweep_expired(oon_world* h, uint64_t player_ndx) {
     CHECK_W(h);
     Team& T = h->team;
+    for (oon_world* w : T) w->last_frame_swept = false;
     if (!T[0]->block || !T[0]->has_mortals) return OON_OK;
+    for (oon_world* w : T) w->last_frame_swept = true;
     return team_sweep(T, uint32_t(player_ndx), nullptr);
 }
 
@@ -1980,7 +2053,13 @@ static int bench_frames_impl(oon_world* h, float dt, uint32_t nsteps, uint64_t f
             if (flush_bytes) CU(T[i], cudaMalloc(&flush[i], flush_bytes));
             for (uint32_t k = 0; k < 2 * nsteps; ++k) CU(T[i], cudaEventCreate(&ev[(size_t(k) * M) + i]));
         }
-        for (uint32_t k = 0; k < nsteps; ++k) {
+        // ONE multi-frame step (the schedule oon_step(w, dt, nsteps) runs, fused launches included) with the flush and the
+        // event pair of every frame hooked in at the frame's boundaries.
+        const FrameHook hook = [&](uint32_t k, int phase) -> int {
+            if (phase == 1) {
+                for (size_t i = 0; i < M; ++i) { USE(T[i]); CU(T[i], cudaEventRecord(ev[(size_t(2 * k + 1) * M) + i], T[i]->stream)); }
+                return OON_OK;
+            }
             for (size_t i = 0; i < M; ++i) {
                 oon_world* w = T[i];
                 USE(w);
@@ -1997,11 +2076,11 @@ static int bench_frames_impl(oon_world* h, float dt, uint32_t nsteps, uint64_t f
                 if (M > 1) for (oon_world* g : T) if (g != w) CU(w, cudaStreamWaitEvent(w->stream, g->ev_grp, 0));
                 CU(w, cudaEventRecord(ev[(size_t(2 * k) * M) + i], w->stream));
             }
-            int src = team_step(T, dt, 1, profs);
-            if (src) return src;
-            for (size_t i = 0; i < M; ++i) { USE(T[i]); CU(T[i], cudaEventRecord(ev[(size_t(2 * k + 1) * M) + i], T[i]->stream)); }
-        }
-        int src = team_sync(T);
+            return OON_OK;
+        };
+        int src = team_step(T, dt, nsteps, profs, &hook);
+        if (src) return src;
+        src = team_sync(T);
         if (src) return src;
         for (uint32_t k = 0; k < nsteps; ++k) {
             float worst = 0.f;
@@ -2149,6 +2228,7 @@ int oon_debug_fetch_removed(oon_world* h, uint32_t* idx, uint64_t capacity, uint
     uint64_t total = 0;
     for (oon_world* w : T) {
         USE(w);
+        if (!w->last_frame_swept) continue;                  // the last frame ran without a sweep (no expiry was possible): nothing was removed
         uint32_t cnt = 0;
         CU(w, cudaMemcpyAsync(&cnt, w->d_removed_count, sizeof cnt, cudaMemcpyDeviceToHost, w->stream));
         SYNC(w);

@@ -119,8 +119,9 @@ constexpr int FX_MAX_SHIFT = 96;     // 24-bit mantissa << 96 = 120 bits
 // `inv` maps a local slot of the exchange buffer to the local body stored there (identity unless sorted).
 
 // AoS (60 B records) <-> SoA
-// mortal_seen (optional): set to 1 if any unpacked body has a finite lifetime
-int launch_unpack_f32(cudaStream_t st, const oon_body_f32* aos, BodySoA soa, uint32_t first, uint32_t count, uint32_t* mortal_seen);
+// minfo (optional, 4 words, zeroed by the caller): what the unpacked bodies can still do — [0] any finite lifetime, [1] any
+// expired body (lifetime <= 0, not Unlimited), [2] ~bits of the smallest positive lifetime (0: none)
+int launch_unpack_f32(cudaStream_t st, const oon_body_f32* aos, BodySoA soa, uint32_t first, uint32_t count, uint32_t* minfo);
 int launch_pack_f32(cudaStream_t st, BodySoA soa, oon_body_f32* aos, uint32_t first, uint32_t count);
 
 // The reference's three body-creating loops on the device: up to n new bodies appended at index *d_n (which is
@@ -158,7 +159,8 @@ int launch_order_block(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint32
 
 // update_intrinsic + pack the shard's slice of the exchange buffer (one thread per slot, one block per tile).
 // body_base = global index of local body 0.  Slots >= n are written dead.
-int launch_intrinsic_pack(cudaStream_t st, BodySoA soa, const uint32_t* inv, const uint32_t* d_n, uint32_t slots,
+// slot_of[body] = slot it was packed into (read by a later launch_integrate that packs in a NEW order).
+int launch_intrinsic_pack(cudaStream_t st, BodySoA soa, const uint32_t* inv, uint32_t* slot_of, const uint32_t* d_n, uint32_t slots,
                           uint32_t body_base, const PackOut& out, StepParams sp, bool do_intrinsic, unsigned long long* counters);
 
 // How the source tiles of the FAST all-pairs pass are grouped (canonical: a function of the world size only, it fixes
@@ -197,7 +199,8 @@ int launch_interact_player_only(cudaStream_t st, const float* tiles, uint32_t nt
 int launch_integrate(cudaStream_t st, BodySoA soa, const uint32_t* inv, const uint32_t* d_n, uint32_t slots, uint32_t body_base,
                      const float4* partial, unsigned long long* acc, uint32_t* touch, const int* fx_scale,
                      StepParams sp, bool apply_pairwise, bool do_global,
-                     bool fuse_next_intrinsic, const PackOut& out, float2* kick_out, unsigned long long* counters);
+                     bool fuse_next_intrinsic, const PackOut& out, float2* kick_out, unsigned long long* counters,
+                     uint32_t* slot_of, bool reorder /* inv changed since the pass that filled acc: a body's sums sit at slot_of[body] */);
 
 // The caller's expired-body sweep (OON.cpp:1089-1095) as a stable device compaction from `src` into `dst`.
 // d_n is updated in place.  removed_idx (optional, capacity removed_cap) gets the indices at removal time.
@@ -211,7 +214,7 @@ int launch_sweep_scan(cudaStream_t st, BodySoA src, const uint32_t* d_n, uint32_
                       void* temp, size_t temp_bytes, int* scratch_i32 /* 3*slots ints */, int* my_runinfo);
 int launch_sweep_compact(cudaStream_t st, BodySoA src, BodySoA dst, uint32_t* d_n, uint32_t slots, const int* runinfo, int rank,
                          void* temp, size_t temp_bytes, int* scratch_i32, uint32_t* removed_idx, uint32_t removed_cap,
-                         uint32_t* d_removed_count, unsigned long long* counters);
+                         uint32_t* d_removed_count, unsigned long long* counters, uint32_t* minfo /* like launch_unpack_f32, for the survivors */);
 
 // render read set: {x, y, r} per body + the colour word
 int launch_render_pack(cudaStream_t st, BodySoA soa, const uint32_t* d_n, uint32_t slots, float* xyr, uint32_t* colors);

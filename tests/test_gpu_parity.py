@@ -321,6 +321,48 @@ def test_shard_local_io_on_one_gpu_equals_upload_download(kat1):
     w.close(); w2.close()
 
 
+@pytest.mark.parametrize("mode", [FAST, EXACT])
+def test_lifetime_aware_schedule_sweeps_only_when_an_expiry_is_possible(mode):
+    """Bodies that can expire bring the sweep (and the plain, unfused schedule) only on frames where the host cannot rule an
+    expiry out: it learns the smallest remaining lifetime at uploads and whenever it fetches the counts, and counts it down.
+    Same results as the oracle throughout; far fewer launches while every mortal is far from its end and after the last one
+    has gone (the flag is not sticky any more)."""
+    bodies = synth.random_cloud(3000, seed=5)
+    bodies["lifetime"][10:60] = 1.0                      # a run of 50: the sweep's skip-after-erase quirk takes several frames
+    bodies["lifetime"][100:110] = 2.0
+    props = dict(friction=0.01, gravity_mode=1, gravity=6.6743e-11, interact_n2n=True, repulsion_stiffness=0.0, collision_mode=1, loop_mode=0)
+    o = make_oracle(bodies, props)
+    w = gpu_world(bodies, props, mode, capture=0)
+
+    def advance(frames):
+        if mode == FAST:
+            w.upload(o.bodies())                         # teacher-forced: same state at the start of every leg
+        l0 = w.launch_count()
+        w.step(DT, frames); o.step(DT, frames)
+        used = w.launch_count() - l0
+        assert w.entity_count() == o.n                   # (fetching the count is also what refreshes the host's knowledge)
+        got, ref = w.download(), o.bodies()
+        if mode == EXACT:
+            ok, field = bodies_equal_except_color(got, ref)
+            assert ok, field
+        else:
+            # free-running FAST legs: lifetimes, expiries and the sweep do not depend on the trajectories (touch decisions may)
+            assert got["lifetime"].tobytes() == ref["lifetime"].tobytes() and got["r"].tobytes() == ref["r"].tobytes()
+        return used
+
+    assert advance(20) <= 20 * 2 + 4                     # no expiry possible: interact + fused integrate per frame, no sweep kernels
+    assert advance(8) <= 8 * 2 + 4
+    crossing = advance(8)                                # frames 28..35: the 1.0 s bodies expire at frame 31
+    assert crossing > 8 * 5 and o.n < 3000
+    advance(30)                                          # ... the 2.0 s ones at frame 61
+    assert o.n == 3000 - 60 + int((o.bodies()["lifetime"] == 0).sum())     # (an expired body may still wait for its turn)
+    while (o.bodies()["lifetime"] == 0).any():
+        advance(2)
+    assert o.n == 2940
+    assert advance(10) <= 10 * 2 + 4                     # nothing mortal is left: back to the immortal schedule
+    w.close()
+
+
 # ---------------------------------------------------------------------------------------------- sizes and edges
 @pytest.mark.parametrize("n", [0, 1, 2, 3, 31, 255, 256, 257, 511, 513, 1500])
 def test_ragged_and_tiny_worlds(n):
