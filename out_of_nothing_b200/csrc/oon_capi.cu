@@ -102,6 +102,8 @@ struct oon_world {
     double life_budget = 0.0;
     bool last_frame_swept = false; // the most recent frame ended with a sweep (oon_debug_fetch_removed: else nothing was removed)
     uint32_t* d_minfo = nullptr;   // [4] lifetime summary written by the unpack / sweep kernels (see note_lifetime)
+    uint32_t* d_work_ctr = nullptr; // [2] work counter of the persistent FAST interact kernel (zero between launches)
+    bool persistent_interact = false;   // OON_K1_PERSISTENT=1: ~592 persistent CTAs draw the work items dynamically (measured slower, see profiles/README.md)
     bool has_mortals = false; // any body with lifetime > 0 or a non-unlimited non-positive lifetime
     uint32_t player_ndx = 0;  // player_entity_ndx(): the sweep inside oon_step tests the bodies after it (OON.cpp:1089)
 
@@ -761,7 +763,8 @@ int do_interact(oon_world* w, const StepParams& sp, Prof* prof) {
         if (sp.n2n)
             launched = launch_interact(w->stream, w->tiles, total_tiles(w), geo, uint32_t(w->rank) * w->block, w->block,
                                        w->d_n, w->soa[w->cur].d, uint32_t(w->rank) * w->block, sp, xv, w->acc, w->touch, w->fx_scale, w->partial,
-                                       w->counters, w->cap, w->dbg_fraction, w->dbg_part, w->dbg_trace, &w->dbg_trace_ctas);
+                                       w->counters, w->cap, w->dbg_fraction, w->dbg_part, w->dbg_trace, &w->dbg_trace_ctas,
+                                       w->persistent_interact ? w->d_work_ctr : nullptr);
         else
             launched = launch_wait_peers(w->stream, xv) +
                        launch_interact_player_only(w->stream, w->tiles, total_tiles(w), uint32_t(w->rank) * w->block, w->block, w->d_n,
@@ -1177,6 +1180,7 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
     if (const char* e = getenv("OON_MORTON_MIN")) { long v = atol(e); if (v >= 0) w->morton_min_bodies = uint64_t(v); }
     if (const char* e = getenv("OON_RESORT_EVERY")) { long v = atol(e); if (v > 0) w->resort_every = uint32_t(v); }
     if (const char* e = getenv("OON_FUSE_REORDER")) w->fuse_reorder = atoi(e) != 0;
+    if (const char* e = getenv("OON_K1_PERSISTENT")) w->persistent_interact = atoi(e) != 0;
     auto bail = [&](int code) { std::string msg = w->error; oon_destroy(w); g_create_error = msg; return code; };
 #define CUB_(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { w->error = std::string(#call) + " failed: " + cudaGetErrorString(e_); return bail(OON_ERR_CUDA); } } while (0)
     CUB_(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
@@ -1195,6 +1199,7 @@ static int create_common(int device, int rank, int nranks, const void* id, oon_w
     CUB_(cudaMemset(w->counters, 0, sizeof(unsigned long long) * C_COUNT));
     CUB_(cudaMalloc(&w->fx_scale, sizeof(int))); CUB_(cudaMemset(w->fx_scale, 0, sizeof(int)));
     CUB_(cudaMalloc(&w->d_minfo, 4 * sizeof(uint32_t))); CUB_(cudaMemset(w->d_minfo, 0, 4 * sizeof(uint32_t)));
+    CUB_(cudaMalloc(&w->d_work_ctr, 2 * sizeof(uint32_t))); CUB_(cudaMemset(w->d_work_ctr, 0, 2 * sizeof(uint32_t)));
     CUB_(cudaMalloc(&w->emit_rec, sizeof(EmitBase) * size_t(nranks))); CUB_(cudaMemset(w->emit_rec, 0, sizeof(EmitBase) * size_t(nranks)));
     {
         const uint32_t init[3] = {0u, 0x7f61b1e6u /* BOX_EMPTY */, 0u};
@@ -1297,7 +1302,7 @@ int oon_destroy(oon_world* w) {
     soa_free(w->soa[0]); soa_free(w->soa[1]);
     cudaFree(w->tiles_buf[0]); cudaFree(w->tiles_buf[1]); cudaFree(w->acc); cudaFree(w->touch); cudaFree(w->fx_scale); cudaFree(w->rank_stats);
     cudaFree(w->flags); if (w->timeouts_host) cudaFreeHost(w->timeouts_host); cudaFree(w->ipc_stage); cudaFree(w->runinfo); cudaFree(w->d_counts); cudaFree(w->partial); cudaFree(w->scratch4); cudaFree(w->kick); cudaFree(w->d_n); cudaFree(w->d_removed_count);
-    cudaFree(w->counters); cudaFree(w->sweep_temp); cudaFree(w->sweep_scratch); cudaFree(w->removed_idx); cudaFree(w->aos_dev); cudaFree(w->emit_rec); cudaFree(w->d_minfo);
+    cudaFree(w->counters); cudaFree(w->sweep_temp); cudaFree(w->sweep_scratch); cudaFree(w->removed_idx); cudaFree(w->aos_dev); cudaFree(w->emit_rec); cudaFree(w->d_minfo); cudaFree(w->d_work_ctr);
     cudaFree(w->xyr_dev); cudaFree(w->cap.coll); cudaFree(w->cap.touch);
     cudaFree(w->inv); cudaFree(w->order_temp); cudaFree(w->order_keys); cudaFree(w->order_vals); cudaFree(w->order_bounds);
     if (w->ev_start) cudaEventDestroy(w->ev_start);

@@ -182,7 +182,8 @@ int launch_interact(cudaStream_t st, const float* tiles, uint32_t ntiles, const 
                     uint32_t target_base, uint32_t slots, const uint32_t* d_n_local, BodySoA soa, uint32_t body_base,
                     StepParams sp, const ExchangeView& xv, unsigned long long* acc, uint32_t* touch, int* fx_scale, float4* partial,
                     unsigned long long* counters, CaptureBuf cap, uint32_t dbg_fraction = 0, uint32_t dbg_part = 0,
-                    unsigned long long* trace = nullptr /* tuning aid: 3 words per CTA */, uint32_t* trace_ctas = nullptr);
+                    unsigned long long* trace = nullptr /* tuning aid: 3 words per CTA */, uint32_t* trace_ctas = nullptr,
+                    uint32_t* work_ctr = nullptr /* FAST: {next item, CTAs finished}, both 0 between launches: persistent CTAs draw their work from it */);
 // Peer-to-peer exchange: hold the stream until every peer's slice of epoch xv.epoch has landed (for the kernels that
 // read the exchange buffer without waiting themselves).
 int launch_wait_peers(cudaStream_t st, const ExchangeView& xv);

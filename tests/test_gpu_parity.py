@@ -649,6 +649,20 @@ def test_fast_result_does_not_depend_on_the_launch_geometry(n):
     assert all(o == outs[0] for o in outs[1:])
 
 
+def test_persistent_interact_kernel_gives_the_same_bits(monkeypatch):
+    """OON_K1_PERSISTENT=1: the same kernel with persistent CTAs drawing their work items from a counter (a launch geometry
+    like any other: the exact accumulation makes the result independent of it)."""
+    bodies, cfg = synth.make("c4_cloud_100k", n=40000)
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("OON_K1_PERSISTENT", flag)
+        w = gpu_world(bodies, cfg["props"], FAST, capture=0)
+        w.step(cfg["dt"], 4)
+        outs.append(w.download().tobytes())
+        w.close()
+    assert outs[0] == outs[1]
+
+
 @pytest.mark.parametrize("scale_m,scale_p", [(1.0, 1.0), (1e-20, 1e-6), (1e8, 1e3), (1e-30, 1.0)])
 def test_fixed_point_window_follows_the_units_of_the_world(scale_m, scale_p):
     """The fixed-point exponent comes from the world's own statistics (smallest mass, largest coordinate): the same
