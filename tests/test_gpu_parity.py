@@ -649,6 +649,34 @@ def test_fast_result_does_not_depend_on_the_launch_geometry(n):
     assert all(o == outs[0] for o in outs[1:])
 
 
+RACE_STRESS = r"""
+import os, sys, hashlib
+sys.path.insert(0, %r)
+from out_of_nothing_b200 import synth
+from out_of_nothing_b200.world import World
+bodies, cfg = synth.make("c4_cloud_100k", n=40000)
+w = World(0); w.set_props(**cfg["props"]); w.upload(bodies)
+w.step(cfg["dt"], 3)
+print(hashlib.sha256(w.download().tobytes()).hexdigest())
+"""
+
+
+def test_barrier_free_ring_survives_warps_thrown_out_of_step():
+    """compute-sanitizer is closed on this pool (profiles/r2_compute_sanitizer_closed_on_this_pool.log), so the race check of
+    the TMA ring is a stress test: every warp of the FAST interact kernel sleeps a pseudo-random time before each tile
+    (OON_DEBUG_JITTER_NS), in the one-item-per-CTA and in the persistent geometry.  A stage refilled before its last reader
+    has left, or read before its bytes have landed, changes the sums; the exact accumulation makes any change visible as a
+    different hash."""
+    import subprocess, sys
+    from helpers import ROOT
+    hashes = []
+    for env in ({}, {"OON_DEBUG_JITTER_NS": "3000"}, {"OON_DEBUG_JITTER_NS": "20000"}, {"OON_DEBUG_JITTER_NS": "5000", "OON_K1_PERSISTENT": "1"}):
+        out = subprocess.run([sys.executable, "-c", RACE_STRESS % ROOT], env={**__import__("os").environ, **env}, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        hashes.append(out.stdout.strip().splitlines()[-1])
+    assert len(set(hashes)) == 1, hashes
+
+
 def test_persistent_interact_kernel_gives_the_same_bits(monkeypatch):
     """OON_K1_PERSISTENT=1: the same kernel with persistent CTAs drawing their work items from a counter (a launch geometry
     like any other: the exact accumulation makes the result independent of it)."""
@@ -711,6 +739,28 @@ def test_written_out_ieee_fast_paths_equal_the_intrinsics():
 
 
 # ---------------------------------------------------------------------------------------------- render sync (row f4)
+def test_render_read_set_equals_the_oracle(kat1):
+    """What render_scene reads per body (OONMainDisplay_sfml.cpp:181-211) — position, radius, colour — against the ORACLE's
+    bodies after the same frames (EXACT mode: bit for bit), including a body that is terminated on the way (r *= 0.1)."""
+    start, _ = kat1
+    bodies = start.bodies.copy()
+    bodies["lifetime"][5] = 0.05                         # terminated in frame 2, swept in the same frame
+    bodies["lifetime"][0] = -1.0
+    o = make_oracle(bodies, smoke_props(start))
+    w = gpu_world(bodies, smoke_props(start), EXACT, capture=0)
+    for frames in (1, 1, 3):
+        o.step(DT, frames); w.step(DT, frames)
+        ref = o.bodies()
+        xyr, col = w.download_render_rgb()
+        assert len(xyr) == len(ref)
+        assert xyr[:, :2].tobytes() == ref["p"].tobytes() and xyr[:, 2].tobytes() == ref["r"].tobytes()
+        assert (col == ref["color"]).all()               # carried through (the T -> colour map is absent from the reference tree)
+        assert w.download_render().tobytes() == xyr.tobytes()
+    assert len(ref) == len(bodies) - 1
+    w.close()
+
+
+
 def test_render_readback_runs_beside_the_next_frames(kat1):
     """oon_download_render_begin/_end: the positions of frame k reach pinned host memory while frames k+1.. are computed."""
     import torch
