@@ -132,6 +132,9 @@ def _mortal_world(kind):
 @pytest.mark.parametrize("kind", ["boundary_runs", "c3_dense"])
 def test_sharded_world_with_expiring_bodies_equals_one_gpu(tmp_path, kind, mode):
     bodies, props, steps, dt = _mortal_world(kind)
+    if mode == capi.MATH_FAST:
+        steps = min(steps, 9)      # free-running FAST runs on different tilings diverge chaotically in these dense worlds (see below): a shorter horizon,
+                                   # still past every scripted expiry run; the exact-decision check is the teacher-forced test further down
     props = {k: (int(v) if isinstance(v, bool) else v) for k, v in props.items()}
     one, xyr1, ev1 = run_sharded(tmp_path, bodies, props, 1, mode, steps, dt)
     nranks = min(gpu_count(), 8)
