@@ -633,8 +633,12 @@ int exchange(oon_world* w, Prof* prof) {
 // ~0.1 ms; bodies of these worlds cross a tile's width in a few frames, so the order is refreshed every
 // `resort_every` frames, default 1).  Small worlds and worlds with mortal bodies keep the identity order.
 bool mortal_frame(const oon_world* w, float dt);
+// (Round 1 fell back to the identity order for any world with mortal bodies: every tile then takes the checked loop, +30 %.  On
+// frames of the mortal schedule the order is now rebuilt from the TRUE positions after every sweep, on the main stream, with the
+// multi-kernel radix-sort pipeline (~85 us at 100 k bodies, 3 % of the frame) — the one-CTA-per-block kernel is for hiding
+// beside the interact kernel, not for the critical path, and an order computed ahead would index bodies the sweep has moved.)
 bool wants_morton(const oon_world* w, const StepParams& sp) {
-    return sp.n2n && !sp.exact && !mortal_frame(w, sp.dt) && w->morton_enabled && w->n_total >= w->morton_min_bodies;
+    return sp.n2n && !sp.exact && w->morton_enabled && w->n_total >= w->morton_min_bodies;
 }
 
 // Make inv[] valid for the coming pack: identity for the reference-order kernels, Morton order of the current
@@ -680,7 +684,7 @@ int ensure_order(oon_world* w, const StepParams& sp, Prof* prof, bool allow_refr
     int rc;
     if (kind == 2 && (rc = ensure_order_buffers(w))) return rc;
     rc = timed(w, prof, 3, [&](int& launched) -> int {
-        if (kind == 2 && order_fits_one_cta(w->cblock) && w->order_one_cta)
+        if (kind == 2 && order_fits_one_cta(w->cblock) && w->order_one_cta && !mortal_frame(w, sp.dt))
             launched = launch_order_block(w->stream, w->soa[w->cur].d, w->d_n, w->block, w->cblock, 0.f, nullptr, w->inv);
         else if (kind == 2)
             launched = launch_order_morton(w->stream, w->soa[w->cur].d, w->d_n, w->block, w->cblock, 0.f, nullptr, w->inv, w->order_temp, w->order_temp_bytes,
@@ -704,6 +708,7 @@ int ensure_order(oon_world* w, const StepParams& sp, Prof* prof, bool allow_refr
 int start_order_ahead(oon_world* w, const StepParams& sp) {
     NvtxRange range("oon/order_ahead");
     if (!w->async_sort || w->resort_every != 1 || !wants_morton(w, sp) || w->order_kind != 2 || w->next_order_pending) return OON_OK;
+    if (mortal_frame(w, sp.dt)) return OON_OK;            // the sweep at the end of this frame shifts indices: the order is rebuilt after it
     int rc = ensure_order_buffers(w);
     if (rc) return rc;
     CU(w, cudaEventRecord(w->ev_main, w->stream));

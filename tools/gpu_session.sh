@@ -1,21 +1,29 @@
-# GPU session script of the moment (development aid; edited per session) — final 8-GPU record of round 2
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 > gpurun_out/r2_final_bench_8gpu.log 2>&1
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 > gpurun_out/r2_final_bench_4gpu.log 2>&1
-timeout 200 python -m pytest tests/test_gpu_group.py -m gpu -q > gpurun_out/r2_final_pytest_group_8gpu.log 2>&1
-timeout 500 python -m pytest tests/test_gpu_multi.py -m gpu -q -k "kat1-0 or boundary_runs or edits or cloud50k-0" > gpurun_out/r2_final_pytest_multi_8gpu.log 2>&1
-H=out_of_nothing_b200/host/oon_headless
-timeout 120 $H --session=tests/golden/kat1_start.state --interact --friction=0.01 --fixed-dt=0.033 --loop-cap=20 --exit-on-finish --session-save-as=gpurun_out/kat1_end_8gpu.state --no-save-compressed --math=exact --gpus=8 --report > gpurun_out/r2_final_headless_8gpu.log 2>&1
-timeout 120 $H --session=tests/golden/kat1_start.state --interact --friction=0.01 --fixed-dt=0.033 --loop-cap=20 --exit-on-finish --session-save-as=gpurun_out/kat1_end_1gpu.state --no-save-compressed --math=exact --gpus=1 --report >> gpurun_out/r2_final_headless_8gpu.log 2>&1
-cmp gpurun_out/kat1_end_8gpu.state gpurun_out/kat1_end_1gpu.state >> gpurun_out/r2_final_headless_8gpu.log 2>&1 && echo "headless --gpus=8 END.state == --gpus=1 END.state (byte for byte)" >> gpurun_out/r2_final_headless_8gpu.log
-timeout 120 $H --bodies=99999 --interact --friction=0 --fixed-dt=0.033 --loop-cap=400 --gpus=8 --report --no-player-antigravity >> gpurun_out/r2_final_headless_8gpu.log 2>&1
-timeout 120 $H --bodies=99999 --interact --friction=0 --fixed-dt=0.033 --loop-cap=400 --gpus=1 --report --no-player-antigravity >> gpurun_out/r2_final_headless_8gpu.log 2>&1
-tail -n 5 gpurun_out/r2_final_pytest_group_8gpu.log
-tail -n 5 gpurun_out/r2_final_pytest_multi_8gpu.log
-cat gpurun_out/r2_final_headless_8gpu.log
+# GPU session script of the moment (development aid; edited per session)
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2_pytest_12.log 2>&1
+tail -n 12 gpurun_out/r2_pytest_12.log
 python - <<'PY'
-import json
-for f in ("gpurun_out/r2_final_bench_8gpu.log","gpurun_out/r2_final_bench_4gpu.log"):
-    d=json.loads([l for l in open(f) if l.startswith("{")][-1])
-    print(f, "value %.4g ms %.4f e2e %.3f ms frac %.3f launches %d"%(d["value"],d["ms_per_step"],d["e2e"]["ms_per_step"],d["roofline"]["frac"],d["gpu_launches"]), d["kernel_ms_per_step"], {k:v for k,v in d["parity_check"].items() if k!="what"})
-    if "c5" in d: print({k:v for k,v in d["c5"].items() if k!="one_gpu"}, d["c5"]["one_gpu"]["ms_per_step"])
+# a 100k-body world with a thrusting player's exhaust: frames/s with the rebuilt curve order vs the identity order (OON_MORTON=0)
+import os, subprocess, sys
+CHILD = r"""
+import os, sys
+sys.path.insert(0, os.getcwd())
+from out_of_nothing_b200 import synth
+from out_of_nothing_b200.world import World
+bodies, cfg = synth.make("c4_cloud_100k")
+bodies = bodies.copy(); bodies["thrust"][0] = [3e32, 0, 1e32, 0]
+w = World(0); w.set_props(**cfg["props"]); w.upload(bodies)
+ecfg = w.emitter_config(particle_lifetime=0.12, create_mass=0, particle_mass_min=1e20, particle_mass_max=3e20, eject_velocity=(0.0, -4e8))
+import time
+for k in range(30):
+    w.emit_particles(0, 5, ecfg, seed=k); w.step(cfg["dt"], 1)
+w.synchronize(); t0 = time.perf_counter()
+for k in range(30, 90):
+    w.emit_particles(0, 5, ecfg, seed=k); w.step(cfg["dt"], 1)
+w.synchronize(); dt_ = time.perf_counter() - t0
+ev = w.drain_events()
+print("%s: %.3f ms/frame, %d bodies, removed %d, checked fraction %.3f" % (os.environ.get("OON_MORTON", "1"), dt_ / 60 * 1e3, w.entity_count(), ev["removed"], ev["warp_tiles_checked"] / max(1, ev["warp_tiles"])))
+"""
+for m in ("1", "0"):
+    out = subprocess.run([sys.executable, "-c", CHILD], env=dict(os.environ, OON_MORTON=m), capture_output=True, text=True)
+    print("OON_MORTON=" + out.stdout.strip(), out.stderr[-300:])
 PY
