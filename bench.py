@@ -137,11 +137,12 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
     from out_of_nothing_b200 import synth
-    cfg_n = args.n or synth.CONFIGS[args.workload]["n"]
-    rate = calibrate_cpu_rate(pyoracle, synth, args.workload)
+    bodies_all, cfg_all = load_workload(args.workload, args.n)
+    cfg_n = bodies_all.shape[0]
+    rate = calibrate_cpu_rate(pyoracle, synth, args.workload if args.workload in synth.CONFIGS else "c2_swarm_10k")
     budget_s = 90.0
     n_sample = args.cpu_sample_bodies or int(min(cfg_n, max(1000, (budget_s * rate / max(1, args.steps + args.warmup)) ** 0.5)))
-    bodies, cfg = synth.make(args.workload, n=cfg_n)
+    bodies, cfg = bodies_all, cfg_all
     bodies = bodies[:n_sample]
     o = pyoracle.OracleWorld(double=False)
     o.set_props(**cfg["props"]); o.set_bodies(bodies)
@@ -402,7 +403,8 @@ def main():
     launches = w.launch_count() - launches0
     ms = R.max(ms)
     n_end = w.entity_count()
-    inter_per_step = sharding.interactions_per_step(n_start)     # no body of this workload can expire unless it says so
+    n_mid = (n_start + n_end) // 2                               # bodies of C3 expire on the way: frames in the middle of the region count
+    inter_per_step = sharding.interactions_per_step(n_mid)
     value = args.steps * inter_per_step / (ms * 1e-3)
 
     # ---- per-kernel device time (events on the launching stream) for the roofline lines
@@ -434,28 +436,43 @@ def main():
     # ---- e2e: the drop-in call sequence with HOST buffers (pinned), copies inside the timed region.  Every rank keeps the
     # host table of the reference's `bodies` vector and moves only its own block: oon_upload_local + oon_step + oon_download_local.
     e2e_steps = max(1, min(args.e2e_steps, args.steps))
-    host_in = torch.empty(n_start * 60, dtype=torch.uint8).pin_memory()
-    host_out = torch.empty(n_start * 60, dtype=torch.uint8).pin_memory()
     cur = w.download()
-    host_in.numpy()[:] = np.frombuffer(cur.tobytes(), dtype=np.uint8)
-    first, count = w.local_range(n_start)
+    n_e2e = len(cur)                                         # bodies may have expired since the timed region began (C3)
+    mortal_world = bool((cur["lifetime"] != -1.0).any())
+    e2e_value = e2e_s = None
+    h2d = d2h = 0
+    if not (mortal_world and world_size > 1):                # (a sharded world with expiring bodies has ragged blocks: no per-rank host table to cycle)
+        host_in = torch.empty(n_e2e * 60, dtype=torch.uint8).pin_memory()
+        host_out = torch.empty(n_e2e * 60, dtype=torch.uint8).pin_memory()
+        host_in.numpy()[:] = np.frombuffer(cur.tobytes(), dtype=np.uint8)
+        first, count = w.local_range(n_e2e)
+        state = {"n": n_e2e, "inter": 0}
 
-    def e2e_frame(src, dst):
-        w.upload_local_ptr(src.data_ptr() + first * 60, count, n_start)
-        w.step(dt, 1)
-        return w.download_local_ptr(dst.data_ptr() + first * 60, count)
+        def e2e_frame(src, dst):
+            n_now = state["n"]
+            if world_size > 1:
+                w.upload_local_ptr(src.data_ptr() + first * 60, count, n_now)
+                w.step(dt, 1)
+                w.download_local_ptr(dst.data_ptr() + first * 60, count)
+            else:
+                w.upload_ptr(src.data_ptr(), n_now)
+                w.step(dt, 1)
+                state["n"] = w.download_ptr(dst.data_ptr(), n_now)      # the sweep may have removed bodies: the next frame uploads what is left
+            state["inter"] += sharding.interactions_per_step(n_now)
 
-    e2e_frame(host_in, host_out)                             # warm (allocations of the staging buffers)
-    R.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_frame(host_in, host_out)
-        host_in, host_out = host_out, host_in               # next frame's input is this frame's output
-    R.barrier()
-    e2e_s = R.max(time.perf_counter() - t0)
-    e2e_value = e2e_steps * sharding.interactions_per_step(n_start) / e2e_s
-    h2d = 60 * n_start                                       # summed over ranks: every rank uploads its own block ...
-    d2h = 60 * n_start                                       # ... and reads its own block back
+        e2e_frame(host_in, host_out)                         # warm (allocations of the staging buffers)
+        host_in, host_out = host_out, host_in
+        state["inter"] = 0
+        R.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_frame(host_in, host_out)
+            host_in, host_out = host_out, host_in           # next frame's input is this frame's output
+        R.barrier()
+        e2e_s = R.max(time.perf_counter() - t0)
+        e2e_value = state["inter"] / e2e_s
+        h2d = 60 * n_e2e                                     # summed over ranks: every rank uploads its own block ...
+        d2h = 60 * n_e2e                                     # ... and reads its own block back
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on one host core, bounded sample
     cpu = None
@@ -513,7 +530,7 @@ def main():
             "kernel_ms_per_step": {k: v / prof_steps for k, v in prof_ms.items()},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "interactions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": e2e_s / e2e_steps * 1e3,
+                    "steps": e2e_steps, "ms_per_step": (e2e_s / e2e_steps * 1e3) if e2e_s else None,
                     "call": ("oon_upload_local(pinned host AoS, own block) + oon_step(dt,1) + oon_download_local(own block) every frame on every rank"
                              if world_size > 1 else "oon_upload(pinned host AoS) + oon_step(dt,1) + oon_download(pinned host AoS) every frame")},
             "gpu_launches": launches,

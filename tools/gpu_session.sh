@@ -1,11 +1,11 @@
-# GPU session script of the moment (development aid; edited per session) — final 8-GPU bench lines (hot loop unrolled 8x)
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 > gpurun_out/r2_final_bench_8gpu.log 2>&1
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 4 --skip-extras > gpurun_out/r2_final_bench_4gpu.log 2>&1
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --skip-extras > gpurun_out/r2_final_bench_2gpu.log 2>&1
-python - <<'PY'
+# GPU session script of the moment (development aid; edited per session): bench lines of the other BASELINE configs
+for wl in c1_kat1 c2_swarm_10k c3_dense_13k; do
+  for m in fast exact; do
+    timeout 200 python bench.py --workload $wl --math $m --steps 100 --warmup 10 --skip-extras > gpurun_out/r2_bench_${wl}_${m}.log 2>&1
+    python - <<PY
 import json
-for f in ("gpurun_out/r2_final_bench_8gpu.log","gpurun_out/r2_final_bench_4gpu.log","gpurun_out/r2_final_bench_2gpu.log"):
-    d=json.loads([l for l in open(f) if l.startswith("{")][-1])
-    print(f, "value %.4g ms %.4f e2e %.3f ms frac %.3f launches %d"%(d["value"],d["ms_per_step"],d["e2e"]["ms_per_step"],d["roofline"]["frac"],d["gpu_launches"]), d["kernel_ms_per_step"], {k:v for k,v in d.get("parity_check",{}).items() if k!="what"})
-    if "c5" in d: print({k:v for k,v in d["c5"].items() if k!="one_gpu"}, d["c5"]["one_gpu"]["ms_per_step"])
+d=json.loads([l for l in open("gpurun_out/r2_bench_${wl}_${m}.log") if l.startswith("{")][-1])
+print("${wl} ${m}: value %.4g ms %.4f e2e %.3f ms frac %.3f launches %d n_end %d"%(d["value"],d["ms_per_step"],d["e2e"]["ms_per_step"],d["roofline"]["frac"],d["gpu_launches"],d["config"]["n_bodies_end"]), d["kernel_ms_per_step"])
 PY
+  done
+done
