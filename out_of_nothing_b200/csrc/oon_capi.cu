@@ -476,8 +476,9 @@ InteractGeometry grouping(const oon_world* w) {
     uint64_t target_blocks = (uint64_t(w->block) + K1_TARGETS_PER_CTA - 1) / K1_TARGETS_PER_CTA;
     if (w->dbg_fraction > 1) target_blocks = (target_blocks + w->dbg_fraction - 1) / w->dbg_fraction;
     const uint64_t slots = uint64_t(w->sm_count) * 4;                         // resident CTAs
-    // long CTAs: ~16 tiles, more for very large worlds (keep the grid below ~64 waves and gridDim.y below 65535)
-    uint64_t g = std::max<uint64_t>(1, 16 / geo.group_tiles);
+    // long CTAs: ~24 tiles (r2 sweep with the final kernel, 100 k bodies: 8 tiles 2.791 ms, 12: 2.774, 16: 2.765, 24: 2.756, 32: 2.757 per
+    // launch; a 1/8 shard: 0.395 / 0.393 / 0.393 / 0.392 / 0.424), more for very large worlds (keep the grid below ~64 waves)
+    uint64_t g = std::max<uint64_t>(1, 24 / geo.group_tiles);
     g = std::max<uint64_t>(g, (target_blocks * nbig + slots * 64 - 1) / (slots * 64));
     g = std::max<uint64_t>(g, (nbig + 50000) / 50001);
     if (w->debug_gpc) g = w->debug_gpc;                                        // tuning experiments only
