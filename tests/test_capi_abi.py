@@ -79,3 +79,23 @@ def test_null_arguments_are_rejected_not_crashed():
     assert L.oon_step(None, 0.1, 1) == capi.ERR_INVALID
     assert L.oon_get_props(None, None) == capi.ERR_INVALID
     assert L.oon_create(0, None) == capi.ERR_INVALID
+
+
+def test_shard_range_is_the_partition_the_library_and_the_python_helper_agree_on():
+    """oon_shard_range (pure function, no device): the block a rank owns in a freshly uploaded world — the same partition as
+    out_of_nothing_b200/sharding.py, tiles the index space, canonical blocks for 1/2/4/8 ranks."""
+    import ctypes
+    from out_of_nothing_b200 import sharding
+    L = capi.load()
+    for n in (0, 1, 255, 256, 257, 1010, 10703, 100000, 1000000):
+        for nranks in (1, 2, 3, 4, 8):
+            at = 0
+            for rank in range(nranks):
+                first, count = ctypes.c_uint64(), ctypes.c_uint64()
+                assert L.oon_shard_range(n, rank, nranks, ctypes.byref(first), ctypes.byref(count)) == capi.OK
+                lo, hi = sharding.shard_range(n, rank, nranks)
+                assert (first.value, first.value + count.value) == (lo, hi)
+                assert first.value == at
+                at += count.value
+            assert at == n
+    assert L.oon_shard_range(10, 2, 2, None, None) == capi.ERR_INVALID
