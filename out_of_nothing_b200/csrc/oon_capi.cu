@@ -685,9 +685,9 @@ int ensure_order(oon_world* w, const StepParams& sp, Prof* prof, bool allow_refr
     int rc;
     if (kind == 2 && (rc = ensure_order_buffers(w))) return rc;
     rc = timed(w, prof, 3, [&](int& launched) -> int {
-        if (kind == 2 && order_fits_one_cta(w->cblock) && w->order_one_cta && !mortal_frame(w, sp.dt))
-            launched = launch_order_block(w->stream, w->soa[w->cur].d, w->d_n, w->block, w->cblock, 0.f, nullptr, w->inv);
-        else if (kind == 2)
+        // (on the critical path — first frame, after edits, after every sweep — the multi-kernel radix-sort pipeline: ~85 us at
+        // 100 k bodies against ~300 us for the one-CTA-per-block kernel, which exists to hide beside the interact kernel; same order)
+        if (kind == 2)
             launched = launch_order_morton(w->stream, w->soa[w->cur].d, w->d_n, w->block, w->cblock, 0.f, nullptr, w->inv, w->order_temp, w->order_temp_bytes,
                                            w->order_keys, w->order_vals, w->order_bounds);
         else
