@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 60 python -m pytest tests/test_gpu_group.py -x -q -m gpu > gpurun_out/final_group_2gpu.log 2>&1; echo "rc $?" >> gpurun_out/final_group_2gpu.log
-timeout 100 python -m pytest tests/test_gpu_multi.py -x -q -m gpu -k "kat1 or edits or boundary_runs" > gpurun_out/final_multi_2gpu.log 2>&1; echo "rc $?" >> gpurun_out/final_multi_2gpu.log
-tail -n 3 gpurun_out/final_group_2gpu.log gpurun_out/final_multi_2gpu.log
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -s 450 -c 240 --csv --log-file gpurun_out/r2_launches_bench_c4.csv python bench.py --steps 20 --warmup 5 > gpurun_out/ncu_bench.log 2>&1; echo "rc $?"
+wc -l gpurun_out/r2_launches_bench_c4.csv; tail -n 2 gpurun_out/ncu_bench.log | head -c 400
