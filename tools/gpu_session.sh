@@ -1,3 +1,5 @@
+# What one gpurun call of this repo usually runs (every command under its own timeout; logs into gpurun_out/).
 mkdir -p gpurun_out
-timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -s 450 -c 240 --csv --log-file gpurun_out/r2_launches_bench_c4.csv python bench.py --steps 20 --warmup 5 > gpurun_out/ncu_bench.log 2>&1; echo "rc $?"
-wc -l gpurun_out/r2_launches_bench_c4.csv; tail -n 2 gpurun_out/ncu_bench.log | head -c 400
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc $?"
+timeout 300 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc $?"; tail -n 2 gpurun_out/pytest_gpu.log
+timeout 200 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc $?"; head -c 400 gpurun_out/bench.json
